@@ -1,0 +1,222 @@
+"""ORACLE (test infrastructure only) -- NeuralODE / FFJORD forward solve and adjoint gradient.
+
+PARITY UNPINNED (see oracle/tsit5.py header).  Follows:
+  * /root/reference/src/neural_de.jl:47-61   NeuralODE call: ODEProblem{false}(dudt, x, tspan, p),
+    solve(prob, Tsit5(); sensealg = InterpolatingAdjoint(ZygoteVJP), kwargs...)
+  * /root/reference/src/neural_de.jl:372-386 AugmentedNDELayer zero-padding of the state dim
+  * /root/reference/src/ffjord.jl:81-136     __ffjord RHS (monte_carlo = true, AutoZygote branch)
+  * /root/reference/src/ffjord.jl:140-178    __forward_ffjord (augment, end state, logpx)
+  * SciMLSensitivity (compat 7.112, /root/reference/Project.toml:70) Interpolating/Backsolve
+    adjoint restated per SURVEY.md section 3.2: backward Tsit5 solve of [lambda; mu; (y)] with
+    discrete-loss jumps at the saved times, mu inside the error norm.
+
+numpy view: states are (B, NS) C-order == Julia (NS, B) column-major.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import tsit5
+from .mlp import MLP
+from .philox import normal
+
+f32 = np.float32
+SENSE_INTERPOLATING, SENSE_BACKSOLVE = 0, 1
+
+
+# ----------------------------------------------------------------------------- problems
+class NodeProblem:
+    """du/dt = model(u, p)  (/root/reference/src/neural_de.jl:50)."""
+
+    def __init__(self, mlp: MLP):
+        self.mlp = mlp
+        self.ns = mlp.dims[0]
+        assert mlp.dims[-1] == mlp.dims[0]
+
+    def f(self, p, y, call, stream):
+        out, cache = self.mlp.forward(p, y)
+        return out, cache
+
+    def vjp(self, p, y, lam, call, stream):
+        """returns (f(y), lam^T df/dy, lam^T df/dp)."""
+        out, cache = self.mlp.forward(p, y)
+        ybar, pbar = self.mlp.vjp(cache, lam)
+        return out, ybar, pbar
+
+
+class FfjordProblem:
+    """state rows [z (D); delta_logp (1)], RHS = [m(z); -e^T J e] with fresh e per RHS call
+    (/root/reference/src/ffjord.jl:85-92,105-115,134)."""
+
+    def __init__(self, mlp: MLP, seed: int, b_offset: int = 0):
+        self.mlp = mlp
+        self.D = mlp.dims[0]
+        self.ns = self.D + 1
+        self.seed = seed
+        self.b_offset = b_offset
+
+    def noise(self, B, call, stream):
+        return normal(self.seed, stream, call, B, self.D, self.b_offset)
+
+    def f(self, p, y, call, stream):
+        z = np.ascontiguousarray(y[:, :self.D])
+        mz, cache = self.mlp.forward(p, z)
+        e = self.noise(z.shape[0], call, stream)
+        eJ, _ = self.mlp.vjp(cache, e, want_dp=False)
+        tr = np.sum(eJ * e, axis=1, dtype=np.float32)
+        out = np.concatenate([mz, -tr[:, None]], axis=1).astype(np.float32)
+        return out, None
+
+    def vjp(self, p, y, lam, call, stream):
+        z = np.ascontiguousarray(y[:, :self.D])
+        lz = np.ascontiguousarray(lam[:, :self.D])
+        ll = lam[:, self.D:self.D + 1]
+        e = self.noise(z.shape[0], call, stream)
+        hL, hdL, cache = self.mlp.jvp_forward(p, z, e)
+        tr = np.sum(hdL * e, axis=1, dtype=np.float32)
+        out = np.concatenate([hL, -tr[:, None]], axis=1).astype(np.float32)
+        zbar, pbar = self.mlp.second_order_vjp(cache, lz, (-ll * e).astype(np.float32))
+        ybar = np.concatenate([zbar, np.zeros_like(ll)], axis=1).astype(np.float32)
+        return out, ybar, pbar
+
+
+# ----------------------------------------------------------------------------- forward
+@dataclass
+class Forward:
+    ts: np.ndarray            # (T,) output times
+    us: np.ndarray            # (T, B, NS)
+    stats: tsit5.Stats
+    sol: tsit5.Solution
+    t0: np.float32
+    t1: np.float32
+
+
+def split_saveat(saveat, t0, t1, save_start=None, save_end=None, save_everystep=None):
+    """OrdinaryDiffEq saveat conventions: the interior points go to the integrator's saveat heap,
+    the ends are governed by save_start / save_end whose defaults depend on saveat."""
+    t0, t1 = f32(t0), f32(t1)
+    if saveat is None:
+        sv = np.zeros(0, dtype=np.float32)
+        scalar = False
+    elif np.isscalar(saveat):
+        h = f32(abs(saveat))
+        n = int(np.floor(float((t1 - t0) / h) + 1e-6))
+        sv = (t0 + h * np.arange(0, n + 1, dtype=np.float32)).astype(np.float32)
+        scalar = True
+    else:
+        sv = np.asarray(saveat, dtype=np.float32)
+        scalar = False
+    if save_everystep is None:
+        save_everystep = sv.size == 0
+    if save_start is None:
+        save_start = bool(save_everystep or sv.size == 0 or scalar or (t0 in sv))
+    if save_end is None:
+        save_end = bool(save_everystep or sv.size == 0 or scalar or (t1 in sv))
+    lo, hi = min(t0, t1), max(t0, t1)
+    interior = np.array([s for s in sv if lo < s < hi], dtype=np.float32)
+    return interior, bool(save_start), bool(save_end), bool(save_everystep)
+
+
+def forward(problem, p, u0, t0, t1, *, saveat=None, save_start=None, save_end=None,
+            save_everystep=None, abstol=1e-6, reltol=1e-3, dense=False, dt0=None,
+            maxiters=100000, record_trace=False, augment=0) -> Forward:
+    u0 = np.asarray(u0, dtype=np.float32)
+    if u0.ndim == 1:
+        u0 = u0[None, :]
+    if augment:
+        u0 = np.concatenate([u0, np.zeros((u0.shape[0], augment), np.float32)], axis=1)
+    interior, ss, se, sev = split_saveat(saveat, t0, t1, save_start, save_end, save_everystep)
+    counter = [0]
+
+    def rhs(state, t):
+        out, _ = problem.f(p, state[0], counter[0], 0)
+        counter[0] += 1
+        return [out]
+
+    sol = tsit5.solve(rhs, [u0], t0, t1, abstol=abstol, reltol=reltol, saveat=interior,
+                      save_start=ss, save_end=se, save_everystep=sev, dense=dense, dt0=dt0,
+                      maxiters=maxiters, record_trace=record_trace)
+    ts = np.array(sol.ts, dtype=np.float32)
+    us = np.stack([u[0] for u in sol.us]) if sol.us else np.zeros((0,) + u0.shape, np.float32)
+    return Forward(ts=ts, us=us, stats=sol.stats, sol=sol, t0=f32(t0), t1=f32(t1))
+
+
+# ----------------------------------------------------------------------------- adjoint
+@dataclass
+class Adjoint:
+    du0: np.ndarray
+    dp: np.ndarray
+    stats: tsit5.Stats
+
+
+def adjoint(problem, p, fwd: Forward, dL_du, *, sensealg=SENSE_INTERPOLATING, abstol=1e-6,
+            reltol=1e-3, maxiters=100000, record_trace=False, augment=0) -> Adjoint:
+    """Backward solve from t1 to t0 of d(lambda)/dt = -(df/dy)^T lambda, d(mu)/dt = -(df/dp)^T lambda
+    (and dy/dt = f for Backsolve) with lambda += dL/du(t_i) at every saved time t_i."""
+    ts = fwd.ts
+    dL = np.asarray(dL_du, dtype=np.float32)
+    assert dL.shape == fwd.us.shape, (dL.shape, fwd.us.shape)
+    t0, t1 = fwd.t0, fwd.t1
+    B, NS = fwd.us.shape[1:]
+    P = p.size
+    counter = [0]
+    jumps = {float(t): i for i, t in enumerate(ts)}
+    interior = [t for t in ts[::-1] if min(t0, t1) < t < max(t0, t1)]
+
+    if sensealg == SENSE_INTERPOLATING:
+        assert fwd.sol.dense, "InterpolatingAdjoint needs the forward dense output"
+
+        def rhs(state, t):
+            y = tsit5.dense_eval(fwd.sol.dense, t)
+            _, ybar, pbar = problem.vjp(p, y, state[0], counter[0], 1)
+            counter[0] += 1
+            return [-ybar, -pbar]
+
+        z0 = [np.zeros((B, NS), np.float32), np.zeros(P, np.float32)]
+    else:
+        def rhs(state, t):
+            out, ybar, pbar = problem.vjp(p, state[2], state[0], counter[0], 1)
+            counter[0] += 1
+            return [-ybar, -pbar, out]
+
+        z0 = [np.zeros((B, NS), np.float32), np.zeros(P, np.float32), fwd.sol.u_final[0].copy()]
+
+    def jump(state, t):
+        i = jumps.get(float(t))
+        if i is None:
+            return None
+        new = list(state)
+        new[0] = (state[0] + dL[i]).astype(np.float32)
+        if sensealg == SENSE_BACKSOLVE:
+            new[2] = fwd.us[i].copy()            # checkpointing = true: reset y to the stored state
+        return new
+
+    def init_jump(state):
+        mod = jump(state, t1)
+        return state if mod is None else mod
+
+    sol = tsit5.solve(rhs, z0, t1, t0, abstol=abstol, reltol=reltol, saveat=(), save_start=False,
+                      save_end=True, save_everystep=False, tstops=interior, on_tstop=jump,
+                      init_jump=init_jump, maxiters=maxiters, record_trace=record_trace)
+    lam, mu = sol.u_final[0], sol.u_final[1]
+    if augment:
+        lam = lam[:, :NS - augment]
+    return Adjoint(du0=lam, dp=mu, stats=sol.stats)
+
+
+# ----------------------------------------------------------------------------- FFJORD wrapper
+def ffjord_logpx(u_end, D):
+    """logpx = logpz - delta_logp with a unit-normal base (/root/reference/src/ffjord.jl:171-176)."""
+    z = u_end[:, :D]
+    logpz = -np.sum(z * z, axis=1, dtype=np.float32) / f32(2.0) - f32(D / 2.0 * np.log(2.0 * np.pi))
+    return (logpz - u_end[:, D]).astype(np.float32)
+
+
+def ffjord_logpx_grad(u_end, D, g):
+    """d/du_end of sum(g * logpx)."""
+    out = np.empty_like(u_end)
+    out[:, :D] = -u_end[:, :D] * g[:, None]
+    out[:, D] = -g
+    return out
