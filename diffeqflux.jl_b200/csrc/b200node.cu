@@ -1,0 +1,927 @@
+// b200node.cu -- C ABI of libb200node.so (see include/b200node.h).
+// Host side: packs the Lux parameter vector, plans shared memory / tiles, owns device memory and
+// launches ONE cooperative persistent kernel per solve.  No CPU fallback exists on purpose.
+#include "../../include/b200node.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "solver.cuh"
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  int smem_optin = 0;
+  std::string err;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Ctrl* ctrl_dev = nullptr;       // control block (device)
+  Ctrl* ctrl_host = nullptr;      // pinned copy of the header part
+  // multi-GPU
+  int rank = 0, world = 1;
+  Mailbox* mailbox = nullptr;     // cudaMalloc'd (IPC-exportable)
+  Mailbox* peers[MAX_RANKS] = {};
+};
+
+struct b200_model {
+  b200_ctx* ctx;
+  MlpDesc m;
+  int wt_total;
+};
+
+struct b200_tape {
+  b200_ctx* ctx = nullptr;
+  MlpDesc m{};
+  int fwd_flavor = FL_FWD_NODE;
+  int sensealg = B200_SENSE_NONE;
+  int B = 0, NS = 0, D = 0, d_in = 0, augment = 0;
+  float t0 = 0, t1 = 0;
+  float* wp = nullptr;
+  float* wtp = nullptr;
+  float* ring = nullptr;
+  int nslots = 0;
+  long long vec_elems = 0;
+  float* k1_first = nullptr;
+  float* step_t = nullptr;
+  int nsteps = 0;
+  int dense = 0;
+  float* out_u = nullptr;    // [n_out][B][NS]
+  float* out_t = nullptr;
+  float* final_state = nullptr;
+  int n_out = 0;
+  std::vector<float> ts;     // host copy of the saved times
+  unsigned long long seed = 0;
+  int noise_per_call = 1;
+  int b_offset = 0;
+};
+
+static int set_err(b200_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return set_err(ctx, B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                     \
+  } while (0)
+
+template <typename Tp>
+static cudaError_t dalloc(b200_ctx* ctx, Tp** p, size_t n) {
+  return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(Tp), ctx->stream);
+}
+static void dfree(b200_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+extern "C" void b200_opts_default(b200_opts* o) {
+  memset(o, 0, sizeof *o);
+  o->abstol = 1e-6f;
+  o->reltol = 1e-3f;
+  o->dt0 = 0.f;
+  o->maxiters = 100000;
+  o->save_start = 1;
+  o->save_end = 1;
+  o->sensealg = B200_SENSE_INTERPOLATING;
+  o->ptr_kind = B200_PTR_HOST;
+  o->noise_per_call = 1;
+}
+
+extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
+  if (!out) return B200_ERR_ARG;
+  *out = nullptr;
+  b200_ctx* ctx = new b200_ctx();
+  ctx->device = device;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    // no CUDA device: fail loudly -- there is no CPU path in this library
+    delete ctx;
+    return B200_ERR_CUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return B200_ERR_CUDA; }
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, device);
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  ctx->stream = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  cudaMalloc(&ctx->ctrl_dev, sizeof(Ctrl));
+  cudaMallocHost(&ctx->ctrl_host, sizeof(Ctrl));
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  const Tableau tab = host_tableau();
+  if (cudaMemcpyToSymbol(c_tab, &tab, sizeof tab) != cudaSuccess) { delete ctx; return B200_ERR_CUDA; }
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < ctx->world; ++r)
+    if (ctx->peers[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peers[r]);
+  if (ctx->mailbox) cudaFree(ctx->mailbox);
+  if (ctx->ctrl_dev) cudaFree(ctx->ctrl_dev);
+  if (ctx->ctrl_host) cudaFreeHost(ctx->ctrl_host);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  delete ctx;
+}
+
+extern "C" const char* b200_last_error(b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" int b200_ctx_sync(b200_ctx* ctx) {
+  if (!ctx) return B200_ERR_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static inline int pad4(int x) { return (x + 3) & ~3; }
+
+extern "C" int b200_model_create(b200_ctx* ctx, int nlayers, const int* dims, const int* acts,
+                                 int pre, b200_model** out) {
+  if (!ctx || !out || !dims || !acts) return B200_ERR_ARG;
+  if (nlayers < 1 || nlayers > MAXL)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "model: %d Dense layers (supported 1..%d)", nlayers, MAXL);
+  if (pre != B200_PRE_NONE && pre != B200_PRE_CUBE)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "model: unknown pre-layer %d", pre);
+  b200_model* mo = new b200_model();
+  mo->ctx = ctx;
+  MlpDesc& m = mo->m;
+  memset(&m, 0, sizeof m);
+  m.nl = nlayers;
+  m.pre = pre;
+  int off = 0, woff = 0, foff = 0;
+  for (int l = 0; l <= nlayers; ++l) {
+    if (dims[l] < 1) { delete mo; return set_err(ctx, B200_ERR_ARG, "model: dims[%d] = %d", l, dims[l]); }
+    m.dims[l] = dims[l];
+    m.dpad[l] = pad4(dims[l]);
+  }
+  for (int l = 0; l < nlayers; ++l) {
+    if (acts[l] < B200_ACT_IDENTITY || acts[l] > B200_ACT_SOFTPLUS) {
+      delete mo;
+      return set_err(ctx, B200_ERR_UNSUPPORTED, "model: unknown activation %d in layer %d", acts[l], l);
+    }
+    m.act[l] = acts[l];
+    m.w_off[l] = off;
+    off += m.dpad[l] * m.dpad[l + 1];
+    m.b_off[l] = off;
+    off += m.dpad[l + 1];
+    m.wt_off[l] = woff;
+    woff += m.dpad[l + 1] * m.dpad[l];
+    m.fw_off[l] = foff;
+    foff += dims[l] * dims[l + 1];
+    m.fb_off[l] = foff;
+    foff += dims[l + 1];
+  }
+  m.ppad = off;
+  m.nparams = foff;
+  mo->wt_total = woff;
+  *out = mo;
+  return 0;
+}
+extern "C" void b200_model_destroy(b200_model* m) { delete m; }
+extern "C" int b200_model_nparams(const b200_model* m) { return m ? m->m.nparams : B200_ERR_ARG; }
+
+// ------------------------------------------------------------------------------------------------ small kernels
+__global__ void pack_params_kernel(MlpDesc m, const float* __restrict__ p, float* __restrict__ wp,
+                                   float* __restrict__ wtp) {
+  const int l = blockIdx.y;
+  const int K = m.dims[l], N = m.dims[l + 1], Kp = m.dpad[l], Np = m.dpad[l + 1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Kp * Np; i += gridDim.x * blockDim.x) {
+    const int k = i / Np, n = i - k * Np;
+    const float v = (k < K && n < N) ? p[m.fw_off[l] + k * N + n] : 0.f;
+    wp[m.w_off[l] + i] = v;
+    wtp[m.wt_off[l] + n * Kp + k] = v;
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < Np; n += gridDim.x * blockDim.x)
+    wp[m.b_off[l] + n] = (n < N) ? p[m.fb_off[l] + n] : 0.f;
+}
+
+__global__ void unpack_grad_kernel(MlpDesc m, const float* __restrict__ g, float* __restrict__ dp,
+                                   int accumulate) {
+  const int l = blockIdx.y;
+  const int K = m.dims[l], N = m.dims[l + 1], Np = m.dpad[l + 1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
+    const int k = i / N, n = i - k * N;
+    const float v = g[m.w_off[l] + k * Np + n];
+    float* o = dp + m.fw_off[l] + i;
+    *o = accumulate ? *o + v : v;
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    float* o = dp + m.fb_off[l] + n;
+    *o = accumulate ? *o + g[m.b_off[l] + n] : g[m.b_off[l] + n];
+  }
+}
+
+// logpx = -sum(z^2)/2 - D/2 log(2 pi) - delta_logp      (src/ffjord.jl:171-176)
+__global__ void ffjord_logpx_kernel(const float* __restrict__ zend, int B, int D, float* __restrict__ logpx) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* z = zend + (long long)b * (D + 1);
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s = fmaf(z[d], z[d], s);
+  logpx[b] = -s / 2.f - (float)(D / 2.0 * 1.8378770664093453) - z[D];
+}
+// cotangent of the end state from the cotangent of logpx
+__global__ void ffjord_seed_kernel(const float* __restrict__ zend, const float* __restrict__ g, int B,
+                                   int D, float* __restrict__ dL) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* z = zend + (long long)b * (D + 1);
+  float* o = dL + (long long)b * (D + 1);
+  for (int d = 0; d < D; ++d) o[d] = -z[d] * g[b];
+  o[D] = -g[b];
+}
+// du0 (first d_in of NV columns) from the final adjoint state
+__global__ void extract_cols_kernel(const float* __restrict__ src, int B, int NV, int ncols,
+                                    float* __restrict__ dst, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * ncols) return;
+  const int b = (int)(i / ncols), c = (int)(i - (long long)b * ncols);
+  const float v = src[(long long)b * NV + c];
+  dst[i] = accumulate ? dst[i] + v : v;
+}
+
+// ------------------------------------------------------------------------------------------------ planning
+static int plan_smem(const MlpDesc& m, int flavor, int TB, SmemPlan& sp) {
+  memset(&sp, 0, sizeof sp);
+  int off = 0;
+  auto take = [&](int floats_per_row) {
+    const int o = off;
+    off += floats_per_row * TB;
+    return o;
+  };
+  for (int l = 0; l < m.nl; ++l) sp.act_off[l] = take(m.dpad[l]);
+  if (flavor != FL_FWD_NODE) sp.dl_off = take(m.dpad[m.nl]);
+  if (flavor == FL_FWD_FFJORD || flavor == FL_ADJ_FFJORD) sp.dl2_off = take(m.dpad[m.nl]);
+  if (m.pre != B200_PRE_NONE) sp.x_off = take(m.dpad[0]);
+  if (flavor == FL_ADJ_FFJORD) {
+    for (int l = 0; l < m.nl; ++l) sp.hd_off[l] = take(m.dpad[l]);
+    for (int l = 1; l < m.nl; ++l) sp.q_off[l] = take(m.dpad[l]);
+    sp.ll_off = take(4);
+  }
+  sp.total = off;
+  return off * (int)sizeof(float);
+}
+
+template <int FL>
+static cudaError_t launch_flavor(const SolveParams& P, int smem_bytes, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  void* args[] = {const_cast<SolveParams*>(&P)};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(solve_kernel<FL>), dim3(P.nctas), dim3(NTHREADS),
+                                     args, (size_t)smem_bytes, stream);
+}
+template <int FL>
+static cudaError_t occupancy_flavor(int smem_bytes, int* blocks_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel<FL>, NTHREADS, (size_t)smem_bytes);
+}
+
+static cudaError_t launch_any(int flavor, const SolveParams& P, int smem_bytes, cudaStream_t s) {
+  switch (flavor) {
+    case FL_FWD_NODE: return launch_flavor<FL_FWD_NODE>(P, smem_bytes, s);
+    case FL_FWD_FFJORD: return launch_flavor<FL_FWD_FFJORD>(P, smem_bytes, s);
+    case FL_ADJ_NODE_INTERP: return launch_flavor<FL_ADJ_NODE_INTERP>(P, smem_bytes, s);
+    case FL_ADJ_NODE_BACKSOLVE: return launch_flavor<FL_ADJ_NODE_BACKSOLVE>(P, smem_bytes, s);
+    default: return launch_flavor<FL_ADJ_FFJORD>(P, smem_bytes, s);
+  }
+}
+static cudaError_t occupancy_any(int flavor, int smem_bytes, int* n) {
+  switch (flavor) {
+    case FL_FWD_NODE: return occupancy_flavor<FL_FWD_NODE>(smem_bytes, n);
+    case FL_FWD_FFJORD: return occupancy_flavor<FL_FWD_FFJORD>(smem_bytes, n);
+    case FL_ADJ_NODE_INTERP: return occupancy_flavor<FL_ADJ_NODE_INTERP>(smem_bytes, n);
+    case FL_ADJ_NODE_BACKSOLVE: return occupancy_flavor<FL_ADJ_NODE_BACKSOLVE>(smem_bytes, n);
+    default: return occupancy_flavor<FL_ADJ_FFJORD>(smem_bytes, n);
+  }
+}
+
+// choose the tile (trajectories per CTA pass) and the grid
+static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int tile_opt, SolveParams& P,
+                      int* smem_bytes) {
+  const int budget = ctx->smem_optin - 2048;   // static __shared__ StepShared lives beside it
+  int best = 0;
+  double best_cost = 1e300;
+  SmemPlan sp;
+  if (tile_opt > 0) {
+    if (tile_opt % 8) return set_err(ctx, B200_ERR_ARG, "opts.tile must be a multiple of 8");
+    if (plan_smem(m, flavor, tile_opt, sp) > budget)
+      return set_err(ctx, B200_ERR_UNSUPPORTED, "opts.tile=%d needs %d B of shared memory (> %d)", tile_opt,
+                     plan_smem(m, flavor, tile_opt, sp), budget);
+    best = tile_opt;
+  } else {
+    for (int TB = 128; TB >= 8; TB >>= 1) {
+      if (plan_smem(m, flavor, TB, sp) > budget) continue;
+      const int ntiles = (B + TB - 1) / TB;
+      const int waves = (ntiles + ctx->num_sms - 1) / ctx->num_sms;
+      const double cost = (double)waves * std::max(TB, 32);
+      if (cost < best_cost) { best_cost = cost; best = TB; }
+    }
+    if (!best)
+      return set_err(ctx, B200_ERR_UNSUPPORTED,
+                     "model too wide for the shared-memory resident path (8 rows need %d B > %d B)",
+                     plan_smem(m, flavor, 8, sp), budget);
+  }
+  *smem_bytes = plan_smem(m, flavor, best, P.sp);
+  P.TB = best;
+  P.ntiles = (B + best - 1) / best;
+  int per_sm = 0;
+  cudaError_t e = occupancy_any(flavor, *smem_bytes, &per_sm);
+  if (e != cudaSuccess) return set_err(ctx, B200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+  if (per_sm < 1) return set_err(ctx, B200_ERR_CUDA, "kernel does not fit on an SM (smem %d B)", *smem_bytes);
+  P.nctas = std::min({P.ntiles, ctx->num_sms * per_sm, MAX_CTAS});
+  return 0;
+}
+
+static void fill_stats(b200_ctx* ctx, const SolveParams& P, float ms, b200_stats* st) {
+  if (!st) return;
+  const Ctrl* c = ctx->ctrl_host;
+  memset(st, 0, sizeof *st);
+  st->retcode = c->retcode;
+  st->naccept = c->naccept;
+  st->nreject = c->nreject;
+  st->nf = c->nf;
+  st->t_final = c->t_final;
+  st->dt_last = c->dt_last;
+  st->tie_dist = c->tie_dist;
+  st->kernel_ms = ms;
+  st->n_out = c->n_out;
+  st->grid = P.nctas;
+  st->tile = P.TB;
+}
+
+// run the persistent kernel, bring the control header back
+static int run_solve(b200_ctx* ctx, int flavor, SolveParams& P, int smem_bytes, b200_stats* st) {
+  P.flavor = flavor;
+  P.ctrl = ctx->ctrl_dev;
+  P.rank = ctx->rank;
+  P.world = ctx->world;
+  for (int r = 0; r < MAX_RANKS; ++r) P.peers[r] = ctx->peers[r];
+  const size_t header = offsetof(Ctrl, partial);
+  CU(cudaMemsetAsync(ctx->ctrl_dev, 0, header, ctx->stream));
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  CU(launch_any(flavor, P, smem_bytes, ctx->stream));
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->ctrl_host, ctx->ctrl_dev, header, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  fill_stats(ctx, P, ms, st);
+  const int rc = ctx->ctrl_host->retcode;
+  if (rc == B200_ERR_TAPE_OVERFLOW)
+    return set_err(ctx, rc, "dense tape overflow after %d accepted steps: raise opts.max_dense_steps",
+                   ctx->ctrl_host->nsteps);
+  if (rc == B200_ERR_TIMEOUT) return set_err(ctx, rc, "grid / peer barrier timed out inside the persistent kernel");
+  return rc;
+}
+
+// stage a caller buffer onto the device (no-op for device pointers)
+static int to_device(b200_ctx* ctx, const float* src, size_t n, int ptr_kind, const float** out,
+                     std::vector<void*>& temps) {
+  if (ptr_kind == B200_PTR_DEVICE || src == nullptr || n == 0) { *out = src; return 0; }
+  float* d = nullptr;
+  CU(dalloc(ctx, &d, n));
+  temps.push_back(d);
+  CU(cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  *out = d;
+  return 0;
+}
+static int from_device(b200_ctx* ctx, float* dst, const float* src, size_t n, int ptr_kind) {
+  if (!dst || n == 0 || dst == src) return 0;
+  CU(cudaMemcpyAsync(dst, src, n * sizeof(float),
+                     ptr_kind == B200_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+static void free_temps(b200_ctx* ctx, std::vector<void*>& temps) {
+  for (void* p : temps) dfree(ctx, p);
+  temps.clear();
+}
+
+extern "C" void b200_tape_free(b200_tape* t) {
+  if (!t) return;
+  b200_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
+  dfree(ctx, t->wp); dfree(ctx, t->wtp); dfree(ctx, t->ring); dfree(ctx, t->k1_first);
+  dfree(ctx, t->step_t); dfree(ctx, t->out_u); dfree(ctx, t->out_t); dfree(ctx, t->final_state);
+  delete t;
+}
+extern "C" int b200_tape_nsteps(const b200_tape* t) { return t ? t->nsteps : B200_ERR_ARG; }
+
+extern "C" int b200_tape_steps(b200_ctx* ctx, const b200_tape* t, float* ts, float* us, int ptr_kind) {
+  if (!ctx || !t) return B200_ERR_ARG;
+  if (!t->dense) return set_err(ctx, B200_ERR_ARG, "tape holds no dense record (sensealg != Interpolating)");
+  CU(cudaSetDevice(ctx->device));
+  const int n = t->nsteps;
+  if (ts) { int rc = from_device(ctx, ts, t->step_t, n + 1, ptr_kind); if (rc) return rc; }
+  if (us) {
+    for (int s = 0; s <= n; ++s) {
+      const float* src = t->ring + ((long long)(s % t->nslots) * 7) * t->vec_elems;
+      int rc = from_device(ctx, us + (long long)s * t->vec_elems, src, (size_t)t->vec_elems, ptr_kind);
+      if (rc) return rc;
+    }
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ forward core
+// u0_dev: [B][d_in] on the device.  Produces a tape that owns every device buffer of the solve.
+static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, const float* p_dev,
+                        const float* u0_dev, int d_in, int augment, int B, float t0, float t1,
+                        const float* saveat_dev, int nsave, const b200_opts* o, b200_stats* st,
+                        b200_tape** tape_out) {
+  const MlpDesc& m = model->m;
+  const int D = m.dims[0];
+  const int NS = (flavor == FL_FWD_FFJORD) ? D + 1 : D;
+  b200_tape* t = new b200_tape();
+  t->ctx = ctx; t->m = m; t->fwd_flavor = flavor; t->sensealg = o->sensealg;
+  t->B = B; t->NS = NS; t->D = D; t->d_in = d_in; t->augment = augment; t->t0 = t0; t->t1 = t1;
+  t->seed = o->seed; t->noise_per_call = o->noise_per_call; t->b_offset = o->b_offset;
+  t->dense = (o->sensealg == B200_SENSE_INTERPOLATING) || o->save_everystep;
+  if (o->save_everystep) nsave = 0;
+  t->vec_elems = (long long)B * NS;
+  const int n_out = (o->save_start ? 1 : 0) + nsave + (o->save_end ? 1 : 0);
+  int rc = 0;
+  SolveParams P{};
+  int smem_bytes = 0;
+  auto fail = [&](int code) { b200_tape_free(t); return code; };
+
+  P.mlp = m;
+  if ((rc = plan_tiles(ctx, m, flavor, B, o->tile, P, &smem_bytes)) != 0) return fail(rc);
+
+  // dense tape capacity
+  int cap = 0;
+  if (t->dense) {
+    cap = o->max_dense_steps;
+    if (cap <= 0) {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const double per_step = 7.0 * (double)t->vec_elems * sizeof(float);
+      const double budget = std::min(0.5 * (double)free_b, 24e9);
+      cap = (int)std::max(16.0, std::min((double)o->maxiters, std::min(4096.0, budget / per_step)));
+    }
+    t->nslots = cap + 1;
+  } else {
+    t->nslots = 2;
+  }
+  cudaError_t e;
+#define TRY(x) if ((e = (x)) != cudaSuccess) return fail(set_err(ctx, B200_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e)))
+  TRY(dalloc(ctx, &t->wp, (size_t)m.ppad));
+  TRY(dalloc(ctx, &t->wtp, (size_t)model->wt_total));
+  TRY(dalloc(ctx, &t->ring, (size_t)t->nslots * 7 * t->vec_elems));
+  TRY(dalloc(ctx, &t->k1_first, (size_t)t->vec_elems));
+  TRY(dalloc(ctx, &t->step_t, (size_t)cap + 2));
+  TRY(dalloc(ctx, &t->out_u, (size_t)std::max(n_out, 1) * t->vec_elems));
+  TRY(dalloc(ctx, &t->out_t, (size_t)n_out + 1));
+  TRY(dalloc(ctx, &t->final_state, (size_t)t->vec_elems));
+  pack_params_kernel<<<dim3(32, m.nl), 256, 0, ctx->stream>>>(m, p_dev, t->wp, t->wtp);
+  TRY(cudaGetLastError());
+
+  P.wp = t->wp; P.wtp = t->wtp;
+  P.B = B; P.NV = NS; P.D = D; P.NS = NS;
+  P.n_norm = (long long)B * ctx->world * NS;
+  P.t0 = t0; P.t1 = t1; P.abstol = o->abstol; P.reltol = o->reltol; P.dt0_user = o->dt0;
+  P.maxiters = o->maxiters;
+  P.ring = t->ring; P.nslots = t->nslots; P.vec_elems = t->vec_elems; P.k1_first = t->k1_first;
+  P.final_state = t->final_state;
+  P.u0 = u0_dev; P.d_in = d_in;
+  P.saveat = saveat_dev; P.nsave = nsave; P.save_start = o->save_start; P.save_end = o->save_end;
+  P.out_u = t->out_u; P.out_t = t->out_t; P.step_t = t->step_t; P.dense = t->dense; P.tape_cap = cap;
+  P.seed = o->seed; P.noise_per_call = o->noise_per_call; P.b_offset = o->b_offset;
+  if (o->save_everystep) { P.save_start = 0; P.save_end = 0; }
+  rc = run_solve(ctx, flavor, P, smem_bytes, st);
+  if (rc < 0) return fail(rc);
+  t->nsteps = ctx->ctrl_host->nsteps;
+  t->n_out = ctx->ctrl_host->n_out;
+  t->ts.resize(t->n_out);
+  if (o->save_everystep) {
+    // saved points = accepted steps (minus the ends the caller declined)
+    std::vector<float> st_h(t->nsteps + 1);
+    if (cudaMemcpyAsync(st_h.data(), t->step_t, st_h.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      return fail(set_err(ctx, B200_ERR_CUDA, "copying step times failed"));
+    t->ts.clear();
+    for (int s = 0; s <= t->nsteps; ++s) {
+      if (s == 0 && !o->save_start) continue;
+      if (s == t->nsteps && !o->save_end && t->nsteps > 0) continue;
+      t->ts.push_back(st_h[s]);
+    }
+    t->n_out = (int)t->ts.size();
+    if (st) st->n_out = t->n_out;
+  } else if (t->n_out) {
+    if (cudaMemcpyAsync(t->ts.data(), t->out_t, t->n_out * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      return fail(set_err(ctx, B200_ERR_CUDA, "copying saved times failed"));
+  }
+#undef TRY
+  *tape_out = t;
+  return rc;
+}
+
+static int check_common(b200_ctx* ctx, const b200_model* model, const b200_opts* o, int B) {
+  if (!ctx) return B200_ERR_ARG;
+  if (!model || !o) return set_err(ctx, B200_ERR_ARG, "null model/opts");
+  if (B < 1) return set_err(ctx, B200_ERR_ARG, "batch %d", B);
+  if (!(o->abstol > 0.f) || !(o->reltol > 0.f)) return set_err(ctx, B200_ERR_ARG, "abstol/reltol must be > 0");
+  if (o->maxiters < 1) return set_err(ctx, B200_ERR_ARG, "maxiters %d", o->maxiters);
+  if (o->ptr_kind != B200_PTR_HOST && o->ptr_kind != B200_PTR_DEVICE) return set_err(ctx, B200_ERR_ARG, "ptr_kind");
+  if (model->m.dims[0] != model->m.dims[model->m.nl])
+    return set_err(ctx, B200_ERR_ARG, "model maps %d -> %d: an ODE right-hand side must preserve the state size",
+                   model->m.dims[0], model->m.dims[model->m.nl]);
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return set_err(ctx, B200_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int b200_node_forward(b200_ctx* ctx, const b200_model* model, const float* p, const float* u0,
+                                 int d_in, int augment, int B, float t0, float t1, const float* saveat,
+                                 int nsave, const b200_opts* o, float* out_u, float* out_t,
+                                 b200_stats* stats, b200_tape** tape) {
+  int rc = check_common(ctx, model, o, B);
+  if (rc) return rc;
+  const MlpDesc& m = model->m;
+  if (!p || !u0) return set_err(ctx, B200_ERR_ARG, "null p/u0");
+  if (d_in < 1 || augment < 0 || d_in + augment != m.dims[0])
+    return set_err(ctx, B200_ERR_ARG, "state size mismatch: d_in %d + augment %d != model input %d", d_in, augment, m.dims[0]);
+  if (nsave < 0 || (nsave > 0 && !saveat)) return set_err(ctx, B200_ERR_ARG, "saveat");
+  if (o->sensealg < B200_SENSE_NONE || o->sensealg > B200_SENSE_BACKSOLVE)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "sensealg %d (supported: InterpolatingAdjoint, BacksolveAdjoint)", o->sensealg);
+  if (o->save_everystep && o->sensealg == B200_SENSE_BACKSOLVE)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "save_everystep with BacksolveAdjoint: pass saveat, or use InterpolatingAdjoint");
+  std::vector<void*> temps;
+  const float *p_d, *u0_d, *sv_d;
+  if ((rc = to_device(ctx, p, (size_t)m.nparams, o->ptr_kind, &p_d, temps))) return rc;
+  if ((rc = to_device(ctx, u0, (size_t)B * d_in, o->ptr_kind, &u0_d, temps))) return rc;
+  // saveat is tiny and always needed by the kernel: copy unless already on the device
+  if ((rc = to_device(ctx, saveat, (size_t)nsave, o->ptr_kind, &sv_d, temps))) return rc;
+  b200_tape* t = nullptr;
+  rc = forward_core(ctx, model, FL_FWD_NODE, p_d, u0_d, d_in, augment, B, t0, t1, sv_d, nsave, o, stats, &t);
+  if (rc >= 0) {
+    int rc2 = 0;
+    if (out_u && !o->save_everystep && (rc2 = from_device(ctx, out_u, t->out_u, (size_t)t->n_out * t->vec_elems, o->ptr_kind))) rc = rc2;
+    if (!rc2 && out_t && !o->save_everystep) {
+      if (o->ptr_kind == B200_PTR_HOST) memcpy(out_t, t->ts.data(), t->ts.size() * sizeof(float));
+      else if ((rc2 = from_device(ctx, out_t, t->out_t, (size_t)t->n_out, o->ptr_kind))) rc = rc2;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    if (tape && (o->sensealg != B200_SENSE_NONE || o->save_everystep) && rc2 == 0) *tape = t;
+    else { b200_tape_free(t); if (tape) *tape = nullptr; }
+  } else if (tape) *tape = nullptr;
+  free_temps(ctx, temps);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ adjoint core
+// dL_dev: [n_out][B][NS] on the device.  Leaves lambda(t0) in *lam_out ([B][NV], caller frees) and the
+// packed mu(t0) in *mu_out.
+static int adjoint_core(b200_ctx* ctx, b200_tape* t, int flavor, const float* dL_dev, const b200_opts* o,
+                        float** lam_out, float** mu_out, b200_stats* st) {
+  const MlpDesc& m = t->m;
+  if (m.act[m.nl - 1] != B200_ACT_IDENTITY)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "adjoint needs an identity output layer (Dense(h => d)); got act %d", m.act[m.nl - 1]);
+  if (flavor == FL_ADJ_FFJORD && m.pre != B200_PRE_NONE)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "FFJORD adjoint does not support a pre-layer");
+  SolveParams P{};
+  int smem_bytes = 0, rc;
+  P.mlp = m;
+  if ((rc = plan_tiles(ctx, m, flavor, t->B, o->tile, P, &smem_bytes)) != 0) return rc;
+  const int NS = t->NS;
+  const int NV = (flavor == FL_ADJ_NODE_BACKSOLVE) ? 2 * NS : NS;
+  const long long vec = (long long)t->B * NV;
+  float *ring = nullptr, *k1 = nullptr, *fin = nullptr, *slabs = nullptr, *mu = nullptr, *muo = nullptr, *ts_d = nullptr;
+  cudaError_t e;
+  auto cleanup = [&]() { dfree(ctx, ring); dfree(ctx, k1); dfree(ctx, slabs); dfree(ctx, mu); dfree(ctx, ts_d); };
+#define TRY(x) if ((e = (x)) != cudaSuccess) { cleanup(); dfree(ctx, fin); dfree(ctx, muo); return set_err(ctx, B200_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e)); }
+  TRY(dalloc(ctx, &ring, (size_t)2 * 7 * vec));
+  TRY(dalloc(ctx, &k1, (size_t)vec));
+  TRY(dalloc(ctx, &fin, (size_t)vec));
+  TRY(dalloc(ctx, &slabs, (size_t)P.nctas * 4 * m.ppad));
+  TRY(dalloc(ctx, &mu, (size_t)2 * m.ppad));
+  TRY(dalloc(ctx, &muo, (size_t)m.ppad));
+  TRY(dalloc(ctx, &ts_d, t->ts.size() + 1));
+  TRY(cudaMemsetAsync(slabs, 0, (size_t)P.nctas * 4 * m.ppad * sizeof(float), ctx->stream));
+  TRY(cudaMemsetAsync(mu, 0, (size_t)2 * m.ppad * sizeof(float), ctx->stream));
+  TRY(cudaMemsetAsync(muo, 0, (size_t)m.ppad * sizeof(float), ctx->stream));
+  if (!t->ts.empty()) TRY(cudaMemcpyAsync(ts_d, t->ts.data(), t->ts.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+
+  P.wp = t->wp; P.wtp = t->wtp;
+  P.B = t->B; P.NV = NV; P.D = t->D; P.NS = NS;
+  P.n_norm = (long long)t->B * ctx->world * NV + m.nparams;
+  P.t0 = t->t1; P.t1 = t->t0;          // integrate backwards
+  P.abstol = o->abstol; P.reltol = o->reltol; P.dt0_user = o->dt0; P.maxiters = o->maxiters;
+  P.ring = ring; P.nslots = 2; P.vec_elems = vec; P.k1_first = k1; P.final_state = fin;
+  P.f_ring = t->ring; P.f_nslots = t->nslots; P.f_nsteps = t->nsteps; P.f_vec_elems = t->vec_elems;
+  P.f_k1_first = t->k1_first; P.f_step_t = t->step_t;
+  P.f_us = t->out_u; P.f_final = t->final_state; P.f_ts = ts_d; P.n_ts = (int)t->ts.size(); P.dL = dL_dev;
+  P.slabs = slabs; P.mu = mu; P.mu_out = muo;
+  P.seed = t->seed; P.noise_per_call = t->noise_per_call; P.b_offset = t->b_offset;
+  rc = run_solve(ctx, flavor, P, smem_bytes, st);
+  cleanup();
+#undef TRY
+  if (rc < 0) { dfree(ctx, fin); dfree(ctx, muo); return rc; }
+  *lam_out = fin;
+  *mu_out = muo;
+  return rc;
+}
+
+extern "C" int b200_node_adjoint(b200_ctx* ctx, const b200_model* model, b200_tape* tape, const float* dL_du,
+                                 const b200_opts* o, float* du0, float* dp, b200_stats* stats) {
+  int rc = check_common(ctx, model, o, tape ? tape->B : 0);
+  if (rc) return rc;
+  if (!tape || !dL_du) return set_err(ctx, B200_ERR_ARG, "null tape/dL_du");
+  if (tape->fwd_flavor != FL_FWD_NODE) return set_err(ctx, B200_ERR_ARG, "tape was not recorded by b200_node_forward");
+  if (tape->sensealg != B200_SENSE_INTERPOLATING && tape->sensealg != B200_SENSE_BACKSOLVE)
+    return set_err(ctx, B200_ERR_ARG, "tape recorded with sensealg %d", tape->sensealg);
+  const int flavor = tape->sensealg == B200_SENSE_INTERPOLATING ? FL_ADJ_NODE_INTERP : FL_ADJ_NODE_BACKSOLVE;
+  std::vector<void*> temps;
+  const float* dL_d;
+  if ((rc = to_device(ctx, dL_du, (size_t)tape->n_out * tape->vec_elems, o->ptr_kind, &dL_d, temps))) return rc;
+  float *lam = nullptr, *mu = nullptr;
+  rc = adjoint_core(ctx, tape, flavor, dL_d, o, &lam, &mu, stats);
+  if (rc >= 0) {
+    const MlpDesc& m = tape->m;
+    const int NV = flavor == FL_ADJ_NODE_BACKSOLVE ? 2 * tape->NS : tape->NS;
+    float *du0_d = nullptr, *dp_d = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (du0) {
+      if (o->ptr_kind == B200_PTR_DEVICE) du0_d = du0; else { e = dalloc(ctx, &du0_d, (size_t)tape->B * tape->d_in); temps.push_back(du0_d); }
+      if (e == cudaSuccess) {
+        const long long n = (long long)tape->B * tape->d_in;
+        extract_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lam, tape->B, NV, tape->d_in, du0_d, 0);
+        if (o->ptr_kind == B200_PTR_HOST) from_device(ctx, du0, du0_d, (size_t)n, B200_PTR_HOST);
+      }
+    }
+    if (dp && e == cudaSuccess) {
+      if (o->ptr_kind == B200_PTR_DEVICE) dp_d = dp; else { e = dalloc(ctx, &dp_d, (size_t)m.nparams); temps.push_back(dp_d); }
+      if (e == cudaSuccess) {
+        unpack_grad_kernel<<<dim3(32, m.nl), 256, 0, ctx->stream>>>(m, mu, dp_d, 0);
+        if (o->ptr_kind == B200_PTR_HOST) from_device(ctx, dp, dp_d, (size_t)m.nparams, B200_PTR_HOST);
+      }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = set_err(ctx, B200_ERR_CUDA, "adjoint output: %s", cudaGetErrorString(e));
+    dfree(ctx, lam);
+    dfree(ctx, mu);
+  }
+  free_temps(ctx, temps);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ FFJORD
+extern "C" int b200_ffjord_forward(b200_ctx* ctx, const b200_model* model, const float* p, const float* x,
+                                   int B, float t0, float t1, const b200_opts* o_in, float* logpx,
+                                   float* z_out, b200_stats* stats, b200_tape** tape) {
+  int rc = check_common(ctx, model, o_in, B);
+  if (rc) return rc;
+  const MlpDesc& m = model->m;
+  if (!p || !x) return set_err(ctx, B200_ERR_ARG, "null p/x");
+  if (m.pre != B200_PRE_NONE) return set_err(ctx, B200_ERR_UNSUPPORTED, "FFJORD does not support a pre-layer");
+  b200_opts o = *o_in;
+  o.save_start = 0;                     // src/ffjord.jl:156: save_everystep=false, save_start=false, save_end=true
+  o.save_end = 1;
+  if (o.sensealg == B200_SENSE_BACKSOLVE) o.sensealg = B200_SENSE_INTERPOLATING;   // hard-wired at src/ffjord.jl:143
+  const int D = m.dims[0];
+  std::vector<void*> temps;
+  const float *p_d, *x_d;
+  if ((rc = to_device(ctx, p, (size_t)m.nparams, o.ptr_kind, &p_d, temps))) return rc;
+  if ((rc = to_device(ctx, x, (size_t)B * D, o.ptr_kind, &x_d, temps))) return rc;
+  b200_tape* t = nullptr;
+  rc = forward_core(ctx, model, FL_FWD_FFJORD, p_d, x_d, D, 1, B, t0, t1, nullptr, 0, &o, stats, &t);
+  if (rc >= 0) {
+    cudaError_t e = cudaSuccess;
+    if (logpx) {
+      float* lp_d = nullptr;
+      if (o.ptr_kind == B200_PTR_DEVICE) lp_d = logpx; else { e = dalloc(ctx, &lp_d, (size_t)B); temps.push_back(lp_d); }
+      if (e == cudaSuccess) {
+        ffjord_logpx_kernel<<<(B + 255) / 256, 256, 0, ctx->stream>>>(t->final_state, B, D, lp_d);
+        if (o.ptr_kind == B200_PTR_HOST) from_device(ctx, logpx, lp_d, (size_t)B, B200_PTR_HOST);
+      }
+    }
+    if (z_out) from_device(ctx, z_out, t->final_state, (size_t)B * (D + 1), o.ptr_kind);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = set_err(ctx, B200_ERR_CUDA, "ffjord output: %s", cudaGetErrorString(e));
+    if (tape && o.sensealg != B200_SENSE_NONE && e == cudaSuccess) *tape = t;
+    else { b200_tape_free(t); if (tape) *tape = nullptr; }
+  } else if (tape) *tape = nullptr;
+  free_temps(ctx, temps);
+  return rc;
+}
+
+extern "C" int b200_ffjord_adjoint(b200_ctx* ctx, const b200_model* model, b200_tape* tape,
+                                   const float* dL_dlogpx, const b200_opts* o, float* dx, float* dp,
+                                   b200_stats* stats) {
+  int rc = check_common(ctx, model, o, tape ? tape->B : 0);
+  if (rc) return rc;
+  if (!tape || !dL_dlogpx) return set_err(ctx, B200_ERR_ARG, "null tape/dL_dlogpx");
+  if (tape->fwd_flavor != FL_FWD_FFJORD || !tape->dense)
+    return set_err(ctx, B200_ERR_ARG, "tape was not recorded by b200_ffjord_forward with InterpolatingAdjoint");
+  const int B = tape->B, D = tape->D;
+  const MlpDesc& m = tape->m;
+  std::vector<void*> temps;
+  const float* g_d;
+  if ((rc = to_device(ctx, dL_dlogpx, (size_t)B, o->ptr_kind, &g_d, temps))) return rc;
+  float* dL_d = nullptr;
+  CU(dalloc(ctx, &dL_d, (size_t)B * (D + 1)));
+  temps.push_back(dL_d);
+  ffjord_seed_kernel<<<(B + 255) / 256, 256, 0, ctx->stream>>>(tape->final_state, g_d, B, D, dL_d);
+  float *lam = nullptr, *mu = nullptr;
+  rc = adjoint_core(ctx, tape, FL_ADJ_FFJORD, dL_d, o, &lam, &mu, stats);
+  if (rc >= 0) {
+    cudaError_t e = cudaSuccess;
+    if (dx) {
+      float* dx_d = nullptr;
+      if (o->ptr_kind == B200_PTR_DEVICE) dx_d = dx; else { e = dalloc(ctx, &dx_d, (size_t)B * D); temps.push_back(dx_d); }
+      if (e == cudaSuccess) {
+        const long long n = (long long)B * D;
+        extract_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lam, B, D + 1, D, dx_d, 0);
+        if (o->ptr_kind == B200_PTR_HOST) from_device(ctx, dx, dx_d, (size_t)n, B200_PTR_HOST);
+      }
+    }
+    if (dp && e == cudaSuccess) {
+      float* dp_d = nullptr;
+      if (o->ptr_kind == B200_PTR_DEVICE) dp_d = dp; else { e = dalloc(ctx, &dp_d, (size_t)m.nparams); temps.push_back(dp_d); }
+      if (e == cudaSuccess) {
+        unpack_grad_kernel<<<dim3(32, m.nl), 256, 0, ctx->stream>>>(m, mu, dp_d, 0);
+        if (o->ptr_kind == B200_PTR_HOST) from_device(ctx, dp, dp_d, (size_t)m.nparams, B200_PTR_HOST);
+      }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = set_err(ctx, B200_ERR_CUDA, "ffjord adjoint output: %s", cudaGetErrorString(e));
+    dfree(ctx, lam);
+    dfree(ctx, mu);
+  }
+  free_temps(ctx, temps);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ multiple shooting
+extern "C" int b200_group_ranges(int datasize, int groupsize, int* first, int* last, int max_groups) {
+  if (!(2 <= groupsize && groupsize <= datasize)) return B200_ERR_ARG;   // DomainError in the reference
+  int g = 0;
+  for (int i = 1; i <= datasize - 1; i += groupsize - 1) {
+    if (g < max_groups && first && last) {
+      first[g] = i - 1;
+      last[g] = std::min(datasize, i + groupsize - 1) - 1;
+    }
+    ++g;
+  }
+  return g;
+}
+
+extern "C" int b200_mshoot_forward(b200_ctx* ctx, const b200_model* model, const float* p,
+                                   const float* ode_data, const float* tsteps, int T, int B, int G,
+                                   const int* first, const int* last, const b200_opts* o_in, float* preds,
+                                   b200_stats* stats, b200_tape** tapes) {
+  int rc = check_common(ctx, model, o_in, B);
+  if (rc) return rc;
+  if (!p || !ode_data || !tsteps || !first || !last || G < 1 || T < 2) return set_err(ctx, B200_ERR_ARG, "mshoot arguments");
+  const MlpDesc& m = model->m;
+  const int D = m.dims[0];
+  b200_opts o = *o_in;
+  o.save_start = 1;
+  o.save_end = 1;
+  std::vector<void*> temps;
+  const float *p_d, *data_d;
+  if ((rc = to_device(ctx, p, (size_t)m.nparams, o.ptr_kind, &p_d, temps))) return rc;
+  if ((rc = to_device(ctx, ode_data, (size_t)T * B * D, o.ptr_kind, &data_d, temps))) return rc;
+  std::vector<float> ts(T);
+  if (o.ptr_kind == B200_PTR_DEVICE) {
+    CU(cudaMemcpyAsync(ts.data(), tsteps, T * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  } else memcpy(ts.data(), tsteps, T * sizeof(float));
+  float* ts_d = nullptr;
+  CU(dalloc(ctx, &ts_d, (size_t)T));
+  temps.push_back(ts_d);
+  CU(cudaMemcpyAsync(ts_d, ts.data(), T * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  int worst = 0;
+  long long row = 0;
+  for (int g = 0; g < G; ++g) {
+    const int a = first[g], b = last[g];
+    if (a < 0 || b >= T || b <= a) { rc = set_err(ctx, B200_ERR_ARG, "group %d range [%d,%d]", g, a, b); break; }
+    const int len = b - a + 1;
+    b200_tape* t = nullptr;
+    rc = forward_core(ctx, model, FL_FWD_NODE, p_d, data_d + (long long)a * B * D, D, 0, B, ts[a], ts[b],
+                      ts_d + a + 1, len - 2, &o, stats ? stats + g : nullptr, &t);
+    if (rc < 0) break;
+    worst = std::max(worst, rc);
+    if (preds) from_device(ctx, preds + row * B * D, t->out_u, (size_t)t->n_out * B * D, o.ptr_kind);
+    row += len;
+    if (tapes && o.sensealg != B200_SENSE_NONE) tapes[g] = t; else { cudaStreamSynchronize(ctx->stream); b200_tape_free(t); }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  free_temps(ctx, temps);
+  return rc < 0 ? rc : worst;
+}
+
+extern "C" int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_tape** tapes, int G,
+                                   const float* dL_dpreds, const b200_opts* o, float* dp, float* d_data,
+                                   b200_stats* stats) {
+  if (!ctx || !tapes || G < 1 || !tapes[0]) return B200_ERR_ARG;
+  int rc = check_common(ctx, model, o, tapes[0]->B);
+  if (rc) return rc;
+  const MlpDesc& m = model->m;
+  const int B = tapes[0]->B, D = tapes[0]->D;
+  std::vector<void*> temps;
+  long long rows = 0;
+  for (int g = 0; g < G; ++g) rows += tapes[g]->n_out;
+  const float* dL_d;
+  if ((rc = to_device(ctx, dL_dpreds, (size_t)rows * B * D, o->ptr_kind, &dL_d, temps))) return rc;
+  float* dp_d = nullptr;
+  if (o->ptr_kind == B200_PTR_DEVICE && dp) dp_d = dp; else { CU(dalloc(ctx, &dp_d, (size_t)m.nparams)); temps.push_back(dp_d); }
+  CU(cudaMemsetAsync(dp_d, 0, m.nparams * sizeof(float), ctx->stream));
+  int worst = 0;
+  long long row = 0;
+  for (int g = 0; g < G; ++g) {
+    b200_tape* t = tapes[g];
+    const int flavor = t->sensealg == B200_SENSE_INTERPOLATING ? FL_ADJ_NODE_INTERP : FL_ADJ_NODE_BACKSOLVE;
+    float *lam = nullptr, *mu = nullptr;
+    rc = adjoint_core(ctx, t, flavor, dL_d + row * B * D, o, &lam, &mu, stats ? stats + g : nullptr);
+    if (rc < 0) break;
+    worst = std::max(worst, rc);
+    unpack_grad_kernel<<<dim3(32, m.nl), 256, 0, ctx->stream>>>(m, mu, dp_d, 1);
+    if (d_data) {
+      // gradient w.r.t. this group's initial condition; groups overlap by one point so the
+      // caller adds it at time index first[g]: we return per-group blocks [G][B][D]
+      const int NV = flavor == FL_ADJ_NODE_BACKSOLVE ? 2 * D : D;
+      float* dst = nullptr;
+      cudaError_t e = cudaSuccess;
+      if (o->ptr_kind == B200_PTR_DEVICE) dst = d_data + (long long)g * B * D;
+      else { e = dalloc(ctx, &dst, (size_t)B * D); temps.push_back(dst); }
+      if (e == cudaSuccess) {
+        const long long n = (long long)B * D;
+        extract_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lam, B, NV, D, dst, 0);
+        if (o->ptr_kind == B200_PTR_HOST) from_device(ctx, d_data + (long long)g * B * D, dst, (size_t)n, B200_PTR_HOST);
+      }
+    }
+    dfree(ctx, lam);
+    dfree(ctx, mu);
+    row += t->n_out;
+  }
+  if (rc >= 0 && dp && o->ptr_kind == B200_PTR_HOST) from_device(ctx, dp, dp_d, (size_t)m.nparams, B200_PTR_HOST);
+  cudaStreamSynchronize(ctx->stream);
+  free_temps(ctx, temps);
+  return rc < 0 ? rc : worst;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU plumbing
+extern "C" int b200_ctx_ipc_export(b200_ctx* ctx, unsigned char handle[B200_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return B200_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->mailbox) {
+    CU(cudaMalloc(&ctx->mailbox, sizeof(Mailbox)));
+    CU(cudaMemset(ctx->mailbox, 0, sizeof(Mailbox)));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) <= B200_IPC_HANDLE_BYTES, "handle size");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->mailbox));
+  memset(handle, 0, B200_IPC_HANDLE_BYTES);
+  memcpy(handle, &h, sizeof h);
+  return 0;
+}
+
+extern "C" int b200_ctx_ipc_import(b200_ctx* ctx, int rank, int world, const unsigned char* handles) {
+  if (!ctx || !handles) return B200_ERR_ARG;
+  if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) return set_err(ctx, B200_ERR_ARG, "rank %d / world %d", rank, world);
+  if (!ctx->mailbox) return set_err(ctx, B200_ERR_ARG, "call b200_ctx_ipc_export first");
+  CU(cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { ctx->peers[r] = ctx->mailbox; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * B200_IPC_HANDLE_BYTES, sizeof h);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peers[r] = reinterpret_cast<Mailbox*>(ptr);
+  }
+  ctx->rank = rank;
+  ctx->world = world;
+  return 0;
+}

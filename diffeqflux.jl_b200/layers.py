@@ -1,0 +1,785 @@
+"""Host-side mirror of DiffEqFlux's Lux-layer API for the NeuralODE hot path.
+
+Same names, argument meaning and error behaviour as the reference (cited per class); every call
+does one C-ABI call into libb200node.so.  Julia is not available in this image, so this Python
+layer plays the role of the `ccall` glue (diffeqflux.jl_b200/julia/B200DiffEqFlux.jl shows the
+Julia side a maintainer would add).
+
+Array convention: a Julia (D, B) column-major matrix is passed here as a (B, D) row-major array --
+the bytes are identical.  `Array(sol)` (D, B, T) is therefore (T, B, D) here.  Parameters are the
+flat ComponentArray [vec(W1); b1; vec(W2); b2; ...] with W (out, in) column-major.
+
+Tensors may be numpy arrays (host pointers, no autograd; use `.pullback`) or torch tensors
+(CUDA tensors go to the library as device pointers; autograd is wired through
+torch.autograd.Function, the stand-in for the ChainRules `rrule` Zygote calls in the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _native as N
+
+try:  # torch is plumbing here (device memory, autograd tape, torch.distributed), not the product
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+# --------------------------------------------------------------------------------------- activations
+def identity(x):
+    return x
+
+
+def tanh(x):
+    return np.tanh(x)
+
+
+def relu(x):
+    return np.maximum(x, 0)
+
+
+def sigmoid(x):
+    return 1 / (1 + np.exp(-x))
+
+
+def softplus(x):
+    return np.log1p(np.exp(x))
+
+
+def cube(x):
+    """`x -> x .^ 3`, the pre-layer of docs/src/examples/neural_ode.md:32."""
+    return x ** 3
+
+
+_ACT_CODES = {identity: N.ACT_IDENTITY, tanh: N.ACT_TANH, relu: N.ACT_RELU, sigmoid: N.ACT_SIGMOID,
+              softplus: N.ACT_SOFTPLUS, None: N.ACT_IDENTITY,
+              "identity": N.ACT_IDENTITY, "tanh": N.ACT_TANH, "relu": N.ACT_RELU,
+              "sigmoid": N.ACT_SIGMOID, "softplus": N.ACT_SOFTPLUS}
+
+
+class UnsupportedError(NotImplementedError):
+    """Raised for configurations outside the B200 hot path (never a silent fallback)."""
+
+
+# --------------------------------------------------------------------------------------- Lux subset
+class Dense:
+    """Lux `Dense(in => out, activation)`: y = act.(W*x .+ b)."""
+
+    def __init__(self, in_dims: int, out_dims: int, activation=identity):
+        if activation not in _ACT_CODES:
+            raise UnsupportedError(f"activation {activation!r}: supported are identity, tanh, relu, sigmoid, softplus")
+        self.in_dims, self.out_dims, self.activation = int(in_dims), int(out_dims), activation
+
+    @property
+    def act_code(self):
+        return _ACT_CODES[self.activation]
+
+
+class Chain:
+    """Lux `Chain(layers...)` restricted to [cube,] Dense, Dense, ... (the models of the hot path)."""
+
+    def __init__(self, *layers):
+        layers = list(layers)
+        self.pre = N.PRE_NONE
+        if layers and layers[0] is cube:
+            self.pre = N.PRE_CUBE
+            layers = layers[1:]
+        if not layers or not all(isinstance(l, Dense) for l in layers):
+            raise UnsupportedError("model must be Chain([x -> x.^3,] Dense, Dense, ...): other Lux layers are outside the B200 path")
+        for a, b in zip(layers[:-1], layers[1:]):
+            if a.out_dims != b.in_dims:
+                raise ValueError(f"DimensionMismatch: Dense({a.in_dims} => {a.out_dims}) then Dense({b.in_dims} => {b.out_dims})")
+        self.layers = layers
+        self.dims = [layers[0].in_dims] + [l.out_dims for l in layers]
+        self.acts = [l.act_code for l in layers]
+
+    @property
+    def nparams(self):
+        return sum(i * o + o for i, o in zip(self.dims[:-1], self.dims[1:]))
+
+    def initialparameters(self, rng) -> np.ndarray:
+        """Flat ComponentArray: glorot-uniform weights, zero biases (Lux defaults)."""
+        out = []
+        for i, o in zip(self.dims[:-1], self.dims[1:]):
+            lim = math.sqrt(6.0 / (i + o))
+            out.append(rng.uniform(-lim, lim, size=i * o).astype(np.float32))
+            out.append(np.zeros(o, np.float32))
+        return np.concatenate(out)
+
+    def axes(self):
+        """ComponentArray axes: {layer_k: {weight: slice, bias: slice}}."""
+        ax, off = {}, 0
+        for k, (i, o) in enumerate(zip(self.dims[:-1], self.dims[1:]), 1):
+            ax[f"layer_{k}"] = {"weight": (slice(off, off + i * o), (o, i)), "bias": (slice(off + i * o, off + i * o + o), (o,))}
+            off += i * o + o
+        return ax
+
+    def view(self, ps, layer: int, name: str):
+        """`ps.layer_k.weight` as an (out, in) view / `ps.layer_k.bias`."""
+        sl, shape = self.axes()[f"layer_{layer}"][name]
+        v = ps[sl]
+        return v.reshape(shape[1], shape[0]).T if name == "weight" else v
+
+
+def setup(rng, layer):
+    """`Lux.setup(rng, layer) -> (ps, st)`; wrapper layers expose the wrapped model's parameters
+    (NeuralDELayer <: AbstractLuxWrapperLayer{:model}, src/neural_de.jl:1)."""
+    model = layer.model if hasattr(layer, "model") else layer
+    ps = model.initialparameters(rng)
+    st = layer.initialstates(rng) if hasattr(layer, "initialstates") else {}
+    return ps, st
+
+
+# --------------------------------------------------------------------------------------- algorithms
+class Tsit5:
+    """OrdinaryDiffEq `Tsit5()` -- the only solver of the B200 path."""
+
+
+@dataclass
+class InterpolatingAdjoint:
+    autojacvec: object = None
+    checkpointing: bool = False
+    code: int = N.SENSE_INTERPOLATING
+
+
+@dataclass
+class BacksolveAdjoint:
+    autojacvec: object = None
+    checkpointing: bool = True
+    code: int = N.SENSE_BACKSOLVE
+
+
+class ZygoteVJP:
+    pass
+
+
+class ReturnCode:
+    Success, MaxIters, DtLessThanMin, Unstable = 0, 1, 2, 3
+
+
+def successful_retcode(rc) -> bool:
+    return rc == 0
+
+
+# --------------------------------------------------------------------------------------- runtime plumbing
+_ctx_cache: dict = {}
+_model_cache: dict = {}
+
+
+def _context(device: int, stream: int = 0) -> N.Context:
+    key = (device, stream)
+    if key not in _ctx_cache:
+        _ctx_cache[key] = N.Context(device, stream or None)
+    return _ctx_cache[key]
+
+
+def _model_handle(ctx: N.Context, chain: Chain):
+    key = (id(ctx), tuple(chain.dims), tuple(chain.acts), chain.pre)
+    if key not in _model_cache:
+        h = C.c_void_p()
+        dims = (C.c_int * len(chain.dims))(*chain.dims)
+        acts = (C.c_int * len(chain.acts))(*chain.acts)
+        ctx.check(N.lib().b200_model_create(ctx._h, len(chain.acts), dims, acts, chain.pre, C.byref(h)))
+        _model_cache[key] = h
+    return _model_cache[key]
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class _Buf:
+    """A float32 buffer the C ABI can read: numpy (host) or torch CUDA (device)."""
+
+    def __init__(self, x, like=None):
+        if _is_torch(x):
+            if x.dtype != torch.float32:
+                raise UnsupportedError(f"eltype {x.dtype}: the B200 path is Float32 only")
+            self.t = x.detach().contiguous()
+            self.dev = self.t.is_cuda
+            if not self.dev:
+                self.a = self.t.numpy()
+            self.ptr = self.t.data_ptr()
+        else:
+            a = np.asarray(x)
+            if a.dtype == np.float64 and like is None:
+                raise UnsupportedError("eltype Float64: the B200 path is Float32 only")
+            self.a = np.ascontiguousarray(a, dtype=np.float32)
+            self.dev = False
+            self.ptr = self.a.ctypes.data
+
+
+def _pick_device(*xs):
+    for x in xs:
+        if _is_torch(x) and x.is_cuda:
+            return x.device.index if x.device.index is not None else torch.cuda.current_device()
+    return 0
+
+
+def _alloc(shape, device_tensor_like, on_device, device):
+    if on_device:
+        return torch.empty(shape, dtype=torch.float32, device=f"cuda:{device}")
+    return np.empty(shape, np.float32)
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    return x.data_ptr() if _is_torch(x) else x.ctypes.data
+
+
+@dataclass
+class SolveStats:
+    nf: int = 0
+    naccept: int = 0
+    nreject: int = 0
+    kernel_ms: float = 0.0
+    tie_dist: float = float("inf")
+    grid: int = 0
+    tile: int = 0
+
+
+class ODESolution:
+    """Minimal `ODESolution`: `.t`, `.u` (list of (B, D) states), `.retcode`, `.stats`,
+    `Array(sol)` = `sol.array()` of shape (T, B, D), `sol[i]`, `sol[-1]`, `len(sol)`."""
+
+    def __init__(self, t, arr, retcode, stats, vector_input=False):
+        self.t = t
+        self._arr = arr
+        self.retcode = retcode
+        self.stats = stats
+        self._vec = vector_input
+
+    def array(self):
+        return self._arr[:, 0, :] if self._vec else self._arr
+
+    @property
+    def u(self):
+        a = self.array()
+        return [a[i] for i in range(a.shape[0])]
+
+    def __getitem__(self, i):
+        return self.array()[i]
+
+    def __len__(self):
+        return self._arr.shape[0]
+
+    def __iter__(self):
+        return iter(self.u)
+
+
+def Array(sol: ODESolution):
+    return sol.array()
+
+
+_SOLVE_KW = {"saveat", "abstol", "reltol", "save_everystep", "save_start", "save_end", "sensealg",
+             "dt", "maxiters", "tile", "max_dense_steps", "dense"}
+
+
+def _split_saveat(saveat, t0, t1, save_start, save_end, save_everystep):
+    """OrdinaryDiffEq conventions (SURVEY.md section 8(c) 'dense output / saveat')."""
+    f32 = np.float32
+    t0, t1 = f32(t0), f32(t1)
+    scalar = False
+    if saveat is None:
+        sv = np.zeros(0, np.float32)
+    elif np.isscalar(saveat):
+        h = f32(abs(saveat))
+        n = int(np.floor(float((t1 - t0) / h) + 1e-6))
+        sv = (t0 + h * np.arange(0, n + 1, dtype=np.float32)).astype(np.float32)
+        scalar = True
+    else:
+        sv = np.asarray(saveat.detach().cpu().numpy() if _is_torch(saveat) else saveat, dtype=np.float32).reshape(-1)
+    if save_everystep is None:
+        save_everystep = sv.size == 0
+    if save_start is None:
+        save_start = bool(save_everystep or sv.size == 0 or scalar or (t0 in sv))
+    if save_end is None:
+        save_end = bool(save_everystep or sv.size == 0 or scalar or (t1 in sv))
+    lo, hi = min(t0, t1), max(t0, t1)
+    interior = np.array([s for s in sv if lo < s < hi], dtype=np.float32)
+    if t1 < t0:
+        interior = interior[::-1].copy()
+    return interior, bool(save_start), bool(save_end), bool(save_everystep) and sv.size == 0
+
+
+class _Solve:
+    """One forward solve through the C ABI plus (optionally) its tape."""
+
+    def __init__(self, chain: Chain, tspan, args, kwargs, augment=0):
+        if len(args) == 0 or args[0] is None:
+            raise UnsupportedError("alg = nothing (DifferentialEquations default algorithm): pass Tsit5()")
+        if not isinstance(args[0], Tsit5) and args[0] is not Tsit5:
+            raise UnsupportedError(f"solver {type(args[0]).__name__}: only Tsit5() runs on the B200 path")
+        if len(args) > 1:
+            raise UnsupportedError("extra positional solve arguments are not supported")
+        bad = set(kwargs) - _SOLVE_KW
+        if bad:
+            raise UnsupportedError(f"unsupported solve keyword(s) {sorted(bad)}")
+        self.chain, self.tspan, self.kw, self.augment = chain, tspan, dict(kwargs), augment
+        sa = self.kw.get("sensealg", InterpolatingAdjoint(autojacvec=ZygoteVJP()))   # src/neural_de.jl:57
+        if isinstance(sa, type):
+            sa = sa()
+        if not isinstance(sa, (InterpolatingAdjoint, BacksolveAdjoint)):
+            raise UnsupportedError(f"sensealg {type(sa).__name__}: supported are InterpolatingAdjoint, BacksolveAdjoint")
+        self.sense = sa.code
+
+    def opts(self, on_device, want_tape):
+        o = N.default_opts()
+        o.abstol = float(self.kw.get("abstol", 1e-6))
+        o.reltol = float(self.kw.get("reltol", 1e-3))
+        o.dt0 = float(self.kw.get("dt", 0.0))
+        o.maxiters = int(self.kw.get("maxiters", 100000))
+        o.tile = int(self.kw.get("tile", 0))
+        o.max_dense_steps = int(self.kw.get("max_dense_steps", 0))
+        o.ptr_kind = N.PTR_DEVICE if on_device else N.PTR_HOST
+        o.sensealg = self.sense if want_tape else N.SENSE_NONE
+        return o
+
+    def forward(self, x, p, want_tape):
+        t0, t1 = self.tspan
+        xb, pb = _Buf(x), _Buf(p)
+        vec = (xb.t.dim() if _is_torch(x) else xb.a.ndim) == 1
+        shape = tuple(xb.t.shape) if _is_torch(x) else xb.a.shape
+        B, d_in = (1, shape[0]) if vec else shape
+        D = d_in + self.augment
+        if D != self.chain.dims[0]:
+            raise ValueError(f"DimensionMismatch: state has {D} rows, model expects {self.chain.dims[0]}")
+        on_dev = xb.dev
+        if pb.dev != on_dev:
+            raise ValueError("u0 and p must live on the same device")
+        dev = _pick_device(x, p)
+        ctx = _context(dev)
+        mh = _model_handle(ctx, self.chain)
+        interior, ss, se, sev = _split_saveat(self.kw.get("saveat"), t0, t1, self.kw.get("save_start"),
+                                              self.kw.get("save_end"), self.kw.get("save_everystep"))
+        o = self.opts(on_dev, want_tape)
+        o.save_start, o.save_end, o.save_everystep = int(ss), int(se), int(sev)
+        if sev and o.sensealg == N.SENSE_BACKSOLVE:
+            raise UnsupportedError("save_everystep=true with BacksolveAdjoint: pass saveat or use InterpolatingAdjoint")
+        st = N.Stats()
+        tape = C.c_void_p()
+        sv = interior
+        if on_dev:
+            sv_t = torch.from_numpy(interior).to(f"cuda:{dev}") if interior.size else None
+            sv_ptr = sv_t.data_ptr() if sv_t is not None else None
+        else:
+            sv_ptr = sv.ctypes.data if sv.size else None
+        n_out = int(ss) + len(interior) + int(se)
+        out_u = None if sev else _alloc((n_out, B, D), x, on_dev, dev)
+        out_t = None if sev else _alloc((n_out,), x, on_dev, dev)
+        need_tape = want_tape or sev
+        rc = ctx.check(N.lib().b200_node_forward(
+            ctx._h, mh, pb.ptr, xb.ptr, d_in, self.augment, B, float(t0), float(t1), sv_ptr, len(interior),
+            C.byref(o), _ptr(out_u), _ptr(out_t), C.byref(st), C.byref(tape) if need_tape else None))
+        if sev:
+            n = N.lib().b200_tape_nsteps(tape)
+            ts = _alloc((n + 1,), x, on_dev, dev)
+            us = _alloc((n + 1, B, D), x, on_dev, dev)
+            ctx.check(N.lib().b200_tape_steps(ctx._h, tape, _ptr(ts), _ptr(us), o.ptr_kind))
+            lo = 0 if ss else 1
+            hi = n + 1 if (se or n == 0) else n
+            out_u, out_t = us[lo:hi], ts[lo:hi]
+            if not want_tape:
+                N.lib().b200_tape_free(tape)
+                tape = C.c_void_p()
+        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile)
+        return dict(ctx=ctx, mh=mh, tape=tape, out_u=out_u, out_t=out_t, rc=rc, stats=stats, vec=vec,
+                    B=B, D=D, d_in=d_in, on_dev=on_dev, dev=dev, opts=o)
+
+    def adjoint(self, fw, dL):
+        """(du0, dp) from the cotangent of the saved states; consumes nothing (tape reusable)."""
+        ctx, o = fw["ctx"], fw["opts"]
+        dLb = _Buf(dL)
+        B, d_in = fw["B"], fw["d_in"]
+        du0 = _alloc((B, d_in), None, fw["on_dev"], fw["dev"])
+        dp = _alloc((self.chain.nparams,), None, fw["on_dev"], fw["dev"])
+        st = N.Stats()
+        rc = ctx.check(N.lib().b200_node_adjoint(ctx._h, fw["mh"], fw["tape"], dLb.ptr, C.byref(o), _ptr(du0),
+                                                 _ptr(dp), C.byref(st)))
+        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile)
+        if fw["vec"]:
+            du0 = du0[0]
+        return du0, dp, rc, stats
+
+
+class _TapeOwner:
+    """Frees the C tape when the last Python reference disappears."""
+
+    def __init__(self, tape):
+        self.tape = tape
+
+    def __del__(self):
+        try:
+            if self.tape:
+                N.lib().b200_tape_free(self.tape)
+        except Exception:
+            pass
+
+
+if torch is not None:
+    class _NodeFn(torch.autograd.Function):
+        """The rrule of `solve` (reference: SciMLSensitivity via src/DiffEqFlux.jl:17-22)."""
+
+        @staticmethod
+        def forward(ctx, x, p, solve, holder):
+            fw = solve.forward(x, p, want_tape=True)
+            holder.update(fw)
+            ctx.solve, ctx.fw, ctx.owner = solve, fw, _TapeOwner(fw["tape"])
+            ctx.x_is_host = not x.is_cuda
+            out = fw["out_u"]
+            if not _is_torch(out):
+                out = torch.from_numpy(out)
+            return out
+
+        @staticmethod
+        def backward(ctx, g):
+            fw = ctx.fw
+            g = g.contiguous()
+            if not fw["on_dev"]:
+                g = g.cpu().numpy()
+            du0, dp, rc, stats = ctx.solve.adjoint(fw, g)
+            fw["adjoint_stats"] = stats
+            fw["adjoint_rc"] = rc
+            if not _is_torch(du0):
+                du0, dp = torch.from_numpy(np.ascontiguousarray(du0)), torch.from_numpy(dp)
+            return du0, dp, None, None
+
+
+# --------------------------------------------------------------------------------------- NeuralODE
+class NeuralODE:
+    """`NeuralODE(model, tspan, alg, args...; kwargs...)` (src/neural_de.jl:35-45) called as
+    `(x, p, st) -> (sol, st)` (src/neural_de.jl:47-61)."""
+
+    def __init__(self, model, tspan, *args, **kwargs):
+        if not isinstance(model, Chain):
+            raise UnsupportedError("model must be a Chain of Dense layers")
+        self.model, self.tspan, self.args, self.kwargs = model, tuple(tspan), args, kwargs
+        self._solve = _Solve(model, self.tspan, args, kwargs, augment=getattr(self, "_augment", 0))
+        self.last = {}
+
+    def __call__(self, x, p, st=None):
+        st = {} if st is None else st
+        needs_grad = _is_torch(x) and _is_torch(p) and torch.is_grad_enabled() and (x.requires_grad or p.requires_grad)
+        if needs_grad:
+            self.last = {}
+            arr = _NodeFn.apply(x, p, self._solve, self.last)
+            fw = self.last
+        else:
+            fw = self._solve.forward(x, p, want_tape=False)
+            self.last = fw
+            arr = fw["out_u"]
+        t = fw["out_t"]
+        return ODESolution(t, arr, fw["rc"], fw["stats"], fw["vec"]), st
+
+    def pullback(self, x, p, st=None):
+        """Zygote.pullback-style: returns (sol, back) with back(dL_du) -> (du0, dp)."""
+        fw = self._solve.forward(x, p, want_tape=True)
+        owner = _TapeOwner(fw["tape"])
+        self.last = fw
+        sol = ODESolution(fw["out_t"], fw["out_u"], fw["rc"], fw["stats"], fw["vec"])
+
+        def back(dL):
+            _ = owner
+            if fw["vec"]:
+                dL = dL.reshape((dL.shape[0], 1, -1))
+            du0, dp, rc, stats = self._solve.adjoint(fw, dL)
+            fw["adjoint_stats"], fw["adjoint_rc"] = stats, rc
+            return du0, dp
+
+        return sol, back
+
+
+class AugmentedNDELayer:
+    """`AugmentedNDELayer(nde, adim)` (src/neural_de.jl:372-386): zero-pad `adim` state rows before the
+    NDE (the padding is fused into the kernel's initial-state load; no gradient flows into the zeros)."""
+
+    def __init__(self, nde: NeuralODE, adim: int):
+        if not isinstance(nde, NeuralODE):
+            raise UnsupportedError("AugmentedNDELayer wraps a NeuralODE on the B200 path")
+        self.nde, self.adim, self.model = nde, int(adim), nde.model
+        self._inner = NeuralODE.__new__(NeuralODE)
+        self._inner._augment = self.adim
+        NeuralODE.__init__(self._inner, nde.model, nde.tspan, *nde.args, **nde.kwargs)
+
+    def __call__(self, x, p, st=None):
+        return self._inner(x, p, st)
+
+    def pullback(self, x, p, st=None):
+        return self._inner.pullback(x, p, st)
+
+    @property
+    def last(self):
+        return self._inner.last
+
+
+# --------------------------------------------------------------------------------------- FFJORD
+if torch is not None:
+    class _FfjordFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, p, layer, seed, holder):
+            fw = layer._forward(x, p, seed, want_tape=True)
+            holder.update(fw)
+            ctx.layer, ctx.fw, ctx.owner = layer, fw, _TapeOwner(fw["tape"])
+            out = fw["logpx"]
+            return out if _is_torch(out) else torch.from_numpy(out)
+
+        @staticmethod
+        def backward(ctx, g):
+            fw = ctx.fw
+            g = g.contiguous().reshape(-1)
+            if not fw["on_dev"]:
+                g = g.cpu().numpy()
+            dx, dp = ctx.layer._adjoint(fw, g)
+            if not _is_torch(dx):
+                dx, dp = torch.from_numpy(dx), torch.from_numpy(dp)
+            return dx, dp, None, None, None
+
+
+class FFJORD:
+    """`FFJORD(model, tspan, input_dims, args...; ad, basedist, kwargs...)` (src/ffjord.jl:52-73),
+    called as `(x, ps, st) -> ((logpx, l1, l2), st)` (src/ffjord.jl:138-178).  Only the branch
+    regularize=false, monte_carlo=true, ad in (nothing, AutoZygote), basedist=nothing is on the B200
+    path; the others raise."""
+
+    def __init__(self, model, tspan, input_dims, *args, ad=None, basedist=None, **kwargs):
+        if not isinstance(model, Chain):
+            raise UnsupportedError("model must be a Chain of Dense layers")
+        if basedist is not None:
+            raise UnsupportedError("basedist: only the unit normal (basedist = nothing) is supported")
+        if ad not in (None, "AutoZygote"):
+            raise UnsupportedError(f"ad = {ad}: only nothing / AutoZygote (VJP Hutchinson estimator)")
+        self.model, self.tspan, self.input_dims, self.args = model, tuple(tspan), input_dims, args
+        self.kwargs = kwargs
+        bad = set(kwargs) - (_SOLVE_KW | {"seed", "noise_per_call"})
+        if bad:
+            raise UnsupportedError(f"unsupported solve keyword(s) {sorted(bad)}")
+        kw = {k: v for k, v in kwargs.items() if k in _SOLVE_KW}
+        self._solve = _Solve(model, self.tspan, args, kw)
+        self.last = {}
+
+    def initialstates(self, rng):
+        return {"model": {}, "regularize": False, "monte_carlo": True,
+                "seed": int(rng.integers(0, 2**62)) if hasattr(rng, "integers") else 0, "calls": 0}
+
+    def _forward(self, x, p, seed, want_tape):
+        xb, pb = _Buf(x), _Buf(p)
+        shape = tuple(xb.t.shape) if _is_torch(x) else xb.a.shape
+        if len(shape) != 2 or shape[1] != self.model.dims[0]:
+            raise ValueError(f"DimensionMismatch: x must be (B, {self.model.dims[0]})")
+        B, D = shape
+        on_dev = xb.dev
+        dev = _pick_device(x, p)
+        ctx = _context(dev)
+        mh = _model_handle(ctx, self.model)
+        o = self._solve.opts(on_dev, want_tape)
+        o.seed = int(seed) & (2**64 - 1)
+        o.noise_per_call = int(self.kwargs.get("noise_per_call", 1))
+        if want_tape:
+            o.sensealg = N.SENSE_INTERPOLATING      # hard-wired at src/ffjord.jl:143
+        st = N.Stats()
+        tape = C.c_void_p()
+        logpx = _alloc((B,), x, on_dev, dev)
+        z = _alloc((B, D + 1), x, on_dev, dev)
+        t0, t1 = self.tspan
+        rc = ctx.check(N.lib().b200_ffjord_forward(ctx._h, mh, pb.ptr, xb.ptr, B, float(t0), float(t1), C.byref(o),
+                                                   _ptr(logpx), _ptr(z), C.byref(st),
+                                                   C.byref(tape) if want_tape else None))
+        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile)
+        return dict(ctx=ctx, mh=mh, tape=tape, logpx=logpx, z=z, rc=rc, stats=stats, B=B, D=D, on_dev=on_dev,
+                    dev=dev, opts=o)
+
+    def _adjoint(self, fw, g):
+        ctx, o = fw["ctx"], fw["opts"]
+        gb = _Buf(g)
+        dx = _alloc((fw["B"], fw["D"]), None, fw["on_dev"], fw["dev"])
+        dp = _alloc((self.model.nparams,), None, fw["on_dev"], fw["dev"])
+        st = N.Stats()
+        rc = ctx.check(N.lib().b200_ffjord_adjoint(ctx._h, fw["mh"], fw["tape"], gb.ptr, C.byref(o), _ptr(dx),
+                                                   _ptr(dp), C.byref(st)))
+        fw["adjoint_stats"] = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile)
+        fw["adjoint_rc"] = rc
+        return dx, dp
+
+    def __call__(self, x, ps, st):
+        if st.get("regularize", False):
+            raise UnsupportedError("regularize = true is outside the B200 path")
+        if not st.get("monte_carlo", True):
+            raise UnsupportedError("monte_carlo = false (exact trace) is outside the B200 path")
+        seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
+        needs_grad = _is_torch(x) and _is_torch(ps) and torch.is_grad_enabled() and (x.requires_grad or ps.requires_grad)
+        if needs_grad:
+            self.last = {}
+            logpx = _FfjordFn.apply(x, ps, self, seed, self.last)
+        else:
+            self.last = self._forward(x, ps, seed, want_tape=False)
+            logpx = self.last["logpx"]
+        logpx = logpx.reshape(1, -1) if not _is_torch(logpx) else logpx.reshape(1, -1)
+        z = self.last["z"]
+        delta_logp = z[:, -1].reshape(1, -1)
+        st2 = dict(st)
+        st2["calls"] = int(st.get("calls", 0)) + 1
+        return (logpx, delta_logp, delta_logp), st2
+
+    def pullback(self, x, ps, st):
+        seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
+        fw = self._forward(x, ps, seed, want_tape=True)
+        owner = _TapeOwner(fw["tape"])
+        self.last = fw
+
+        def back(g):
+            _ = owner
+            return self._adjoint(fw, np.asarray(g, np.float32).reshape(-1) if not _is_torch(g) else g.reshape(-1))
+
+        return fw["logpx"], back
+
+
+# --------------------------------------------------------------------------------------- multiple shooting
+def group_ranges(datasize: int, groupsize: int):
+    """`group_ranges(datasize, groupsize)` (src/multiple_shooting.jl:231-239) as 0-based inclusive
+    (first, last) pairs; raises DomainError-like ValueError on a bad groupsize."""
+    if not (2 <= groupsize <= datasize):
+        raise ValueError("DomainError: datasize must be positive and groupsize must to be within [2, datasize]")
+    n = N.lib().b200_group_ranges(datasize, groupsize, None, None, 0)
+    first = (C.c_int * n)()
+    last = (C.c_int * n)()
+    N.lib().b200_group_ranges(datasize, groupsize, first, last, n)
+    return [(first[i], last[i]) for i in range(n)]
+
+
+def _default_continuity_loss(u_end, u_0):
+    """`sum(abs, u_end - u_0)` (src/multiple_shooting.jl:243)."""
+    return (u_end - u_0).abs().sum() if _is_torch(u_end) else np.abs(u_end - u_0).sum()
+
+
+@dataclass
+class ODEProblem:
+    """`ODEProblem(f, u0, tspan, p)` where f is a Chain (the NN right-hand side of a NeuralODE)."""
+    f: Chain
+    u0: object
+    tspan: tuple
+    p: object = None
+    kwargs: dict = field(default_factory=dict)
+
+
+if torch is not None:
+    class _MshootFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, p, data, run):
+            preds, tapes, stats, rc = run.forward(p, data)
+            ctx.run, ctx.tapes = run, tapes
+            ctx.owner = [_TapeOwner(t) for t in tapes]
+            run.retcode, run.stats = rc, stats
+            return preds if _is_torch(preds) else torch.from_numpy(preds)
+
+        @staticmethod
+        def backward(ctx, g):
+            g = g.contiguous()
+            run = ctx.run
+            if not run.on_dev:
+                g = g.cpu().numpy()
+            dp = run.adjoint(ctx.tapes, g)
+            if not _is_torch(dp):
+                dp = torch.from_numpy(dp)
+            return dp, None, None
+
+
+class _MshootRun:
+    def __init__(self, chain, tsteps, ranges, solve: _Solve):
+        self.chain, self.ranges, self.solve = chain, ranges, solve
+        self.tsteps = np.ascontiguousarray(np.asarray(tsteps.detach().cpu().numpy() if _is_torch(tsteps) else tsteps, np.float32))
+        self.retcode, self.stats = 0, None
+
+    def forward(self, p, data):
+        pb, db = _Buf(p), _Buf(data)
+        shape = tuple(db.t.shape) if _is_torch(data) else db.a.shape
+        T, B, D = shape
+        self.on_dev, self.dev = db.dev, _pick_device(data, p)
+        if pb.dev != db.dev:
+            raise ValueError("p and ode_data must live on the same device")
+        ctx = _context(self.dev)
+        mh = _model_handle(ctx, self.chain)
+        self.ctx, self.mh, self.B, self.D = ctx, mh, B, D
+        G = len(self.ranges)
+        o = self.solve.opts(self.on_dev, True)
+        self.opts = o
+        first = (C.c_int * G)(*[a for a, _ in self.ranges])
+        last = (C.c_int * G)(*[b for _, b in self.ranges])
+        rows = sum(b - a + 1 for a, b in self.ranges)
+        preds = _alloc((rows, B, D), None, self.on_dev, self.dev)
+        stats = (N.Stats * G)()
+        tapes = (C.c_void_p * G)()
+        if self.on_dev:
+            ts_dev = torch.from_numpy(self.tsteps).to(f"cuda:{self.dev}")
+            ts_ptr = ts_dev.data_ptr()
+        else:
+            ts_ptr = self.tsteps.ctypes.data
+        rc = ctx.check(N.lib().b200_mshoot_forward(ctx._h, mh, pb.ptr, db.ptr, ts_ptr, T, B, G, first, last, C.byref(o),
+                                                   _ptr(preds), stats, tapes))
+        return preds, [C.c_void_p(t) for t in tapes], [s.as_dict() for s in stats], rc
+
+    def adjoint(self, tapes, g):
+        gb = _Buf(g)
+        G = len(tapes)
+        arr = (C.c_void_p * G)(*[t.value for t in tapes])
+        dp = _alloc((self.chain.nparams,), None, self.on_dev, self.dev)
+        stats = (N.Stats * G)()
+        self.ctx.check(N.lib().b200_mshoot_adjoint(self.ctx._h, self.mh, arr, G, gb.ptr, C.byref(self.opts), _ptr(dp),
+                                                   None, stats))
+        self.adjoint_stats = [s.as_dict() for s in stats]
+        return dp
+
+
+def multiple_shoot(p, ode_data, tsteps, prob: ODEProblem, loss_function, *rest, continuity_term=100, **kwargs):
+    """`multiple_shoot(p, ode_data, tsteps, prob, loss_function, [continuity_loss], solver, group_size;
+    continuity_term = 100, kwargs...)` (src/multiple_shooting.jl:36-94) -> (loss, group_predictions).
+
+    `ode_data` is (T, B, D) (Julia (D, B, T)) or (T, D).  All groups are solved by ONE C-ABI call;
+    the loss callbacks run on the host framework (torch), whose autograd chains into the adjoint."""
+    if len(rest) == 3:
+        continuity_loss, solver, group_size = rest
+    elif len(rest) == 2:
+        continuity_loss = _default_continuity_loss
+        solver, group_size = rest
+    else:
+        raise TypeError("multiple_shoot(p, ode_data, tsteps, prob, loss_function, [continuity_loss], solver, group_size)")
+    nd = ode_data.dim() if _is_torch(ode_data) else np.asarray(ode_data).ndim
+    squeeze = nd == 2
+    data3 = ode_data[:, None, :] if squeeze else ode_data
+    datasize = data3.shape[0]
+    if group_size < 2 or group_size > datasize:
+        raise ValueError("DomainError: group_size can't be < 2 or > number of data points")
+    ranges = group_ranges(datasize, group_size)
+    kw = dict(prob.kwargs)
+    kw.update(kwargs)
+    solve = _Solve(prob.f, prob.tspan, (solver,), kw)
+    run = _MshootRun(prob.f, tsteps, ranges, solve)
+    use_torch = _is_torch(p) and _is_torch(data3)
+    if use_torch:
+        preds = _MshootFn.apply(p, data3, run)
+    else:
+        preds, tapes, stats, rc = run.forward(p, data3)
+        run.retcode, run.stats = rc, stats
+        for t in tapes:
+            N.lib().b200_tape_free(t)
+    group_predictions, row = [], 0
+    for a, b in ranges:
+        n = b - a + 1
+        g = preds[row:row + n]
+        group_predictions.append(g[:, 0, :] if squeeze else g)
+        row += n
+    multiple_shoot.last = run
+    if not successful_retcode(run.retcode):          # src/multiple_shooting.jl:66-67
+        return float("inf"), group_predictions
+    loss = 0
+    for i, (a, b) in enumerate(ranges):
+        u = ode_data[a:b + 1]
+        uh = group_predictions[i]
+        loss = loss + loss_function(u, uh)
+        if i > 0:
+            loss = loss + continuity_term * continuity_loss(group_predictions[i - 1][-1], u[0])
+    return loss, group_predictions
