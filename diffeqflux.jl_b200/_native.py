@@ -65,6 +65,7 @@ _SIGNATURES = {
     "b200_last_error": (C.c_char_p, [_vp]),
     "b200_ctx_sync": (C.c_int, [_vp]),
     "b200_opts_default": (None, [C.POINTER(Opts)]),
+    "b200_ctx_trace": (C.c_int, [_vp, C.c_int, _fp, C.c_int]),
     "b200_model_create": (C.c_int, [_vp, C.c_int, _ip, _ip, C.c_int, C.POINTER(_vp)]),
     "b200_model_destroy": (None, [_vp]),
     "b200_model_nparams": (C.c_int, [_vp]),
@@ -135,6 +136,13 @@ class Context:
         if rc < 0:
             raise B200Error(rc, lib().b200_last_error(self._h).decode())
         return rc
+
+    def trace(self, capacity: int = -1, max_entries: int = 1 << 16):
+        """Enable (capacity > 0) / read the (t, dt, EEst, accepted) trace of the last solve."""
+        import numpy as np
+        buf = np.zeros((max_entries, 4), np.float32)
+        n = self.check(lib().b200_ctx_trace(self._h, capacity, buf.ctypes.data, max_entries))
+        return buf[:n]
 
     def close(self):
         if self._h:

@@ -31,6 +31,10 @@ struct b200_ctx {
   int rank = 0, world = 1;
   Mailbox* mailbox = nullptr;     // cudaMalloc'd (IPC-exportable)
   Mailbox* peers[MAX_RANKS] = {};
+  // diagnostics
+  float* trace_dev = nullptr;
+  int trace_cap = 0;
+  int trace_n = 0;
 };
 
 struct b200_model {
@@ -147,11 +151,34 @@ extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
   for (int r = 0; r < ctx->world; ++r)
     if (ctx->peers[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peers[r]);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
+  if (ctx->trace_dev) cudaFree(ctx->trace_dev);
   if (ctx->ctrl_dev) cudaFree(ctx->ctrl_dev);
   if (ctx->ctrl_host) cudaFreeHost(ctx->ctrl_host);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   delete ctx;
+}
+
+extern "C" int b200_ctx_trace(b200_ctx* ctx, int capacity, float* out, int max_entries) {
+  if (!ctx) return B200_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (capacity >= 0 && capacity != ctx->trace_cap) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->trace_dev) CU(cudaFree(ctx->trace_dev));
+    ctx->trace_dev = nullptr;
+    ctx->trace_cap = 0;
+    ctx->trace_n = 0;
+    if (capacity > 0) {
+      CU(cudaMalloc(&ctx->trace_dev, (size_t)capacity * 4 * sizeof(float)));
+      ctx->trace_cap = capacity;
+    }
+  }
+  const int n = std::min(ctx->trace_n, max_entries);
+  if (out && n > 0) {
+    CU(cudaMemcpyAsync(out, ctx->trace_dev, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
 }
 
 extern "C" const char* b200_last_error(b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
@@ -386,6 +413,8 @@ static int run_solve(b200_ctx* ctx, int flavor, SolveParams& P, int smem_bytes, 
   P.rank = ctx->rank;
   P.world = ctx->world;
   for (int r = 0; r < MAX_RANKS; ++r) P.peers[r] = ctx->peers[r];
+  P.trace = ctx->trace_dev;
+  P.trace_cap = ctx->trace_cap;
   const size_t header = offsetof(Ctrl, partial);
   CU(cudaMemsetAsync(ctx->ctrl_dev, 0, header, ctx->stream));
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -396,6 +425,7 @@ static int run_solve(b200_ctx* ctx, int flavor, SolveParams& P, int smem_bytes, 
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   fill_stats(ctx, P, ms, st);
+  ctx->trace_n = std::min(ctx->trace_cap, ctx->ctrl_host->naccept + ctx->ctrl_host->nreject);
   const int rc = ctx->ctrl_host->retcode;
   if (rc == B200_ERR_TAPE_OVERFLOW)
     return set_err(ctx, rc, "dense tape overflow after %d accepted steps: raise opts.max_dense_steps",

@@ -123,6 +123,8 @@ struct SolveParams {
   int rank, world;
   Mailbox* peers[MAX_RANKS];
   Ctrl* ctrl;
+  float* trace;      // optional [trace_cap][4] = (t, dt, EEst, accepted) per attempted step
+  int trace_cap;
 };
 
 // ------------------------------------------------------------------------------------ tableau
@@ -1087,17 +1089,17 @@ struct Solver {
     const int lo = cta * chunk, hi = min(pp, lo + chunk);
     double part = 0.0;
     for (int j = lo + tid; j < hi; j += NTHREADS) {
-      float tot = 0.f;
+      double tot = 0.0;
       for (int cidx = 0; cidx < P.nctas; ++cidx) {
         const float* sx = P.slabs + ((long long)cidx * 4 + wx) * pp;
-        float v = c1 * __ldcg(sx + j);
+        double v = (double)c1 * (double)__ldcg(sx + j);
         if (wy >= 0) {
           const float* sy = P.slabs + ((long long)cidx * 4 + wy) * pp;
-          v = fmaf(c2, __ldcg(sy + j), v);
+          v += (double)c2 * (double)__ldcg(sy + j);
         }
         tot += v;
       }
-      part += (double)f(j, tot);
+      part += (double)f(j, (float)tot);
     }
     return part;
   }

@@ -293,11 +293,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
       const int lo = cta * chunk, hi = min(pp, lo + chunk);
       float a = 0.f;
       for (int j = lo + tid; j < hi; j += NTHREADS) {
-        float totA = 0.f, totE = 0.f;
+        double dA = 0.0, dE = 0.0;      // fp64: the cross-CTA order must not add rounding noise
         for (int c2 = 0; c2 < P.nctas; ++c2) {
-          totA += __ldcg(P.slabs + ((long long)c2 * 4 + 0) * pp + j);
-          totE += __ldcg(P.slabs + ((long long)c2 * 4 + 1) * pp + j);
+          dA += (double)__ldcg(P.slabs + ((long long)c2 * 4 + 0) * pp + j);
+          dE += (double)__ldcg(P.slabs + ((long long)c2 * 4 + 1) * pp + j);
         }
+        const float totA = (float)dA, totE = (float)dE;
         const float m0 = mu[j];
         const float m1 = fmaf(dt, totA, m0);
         mun[j] = m1;
@@ -327,6 +328,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
           q = fmaxf(inv_qmax, fminf(inv_qmin, __fdiv_rn(q, gamma)));
         }
         ss.tie = fminf(ss.tie, fabsf(EEst - 1.f));
+        if (P.trace && cta == 0 && ss.iter <= P.trace_cap) {
+          float* tr = P.trace + (long long)(ss.iter - 1) * 4;
+          tr[0] = t; tr[1] = dt; tr[2] = EEst; tr[3] = EEst <= 1.f ? 1.f : 0.f;
+        }
         if (EEst <= 1.f) {
           ss.accept = 1;
           ss.naccept += 1;

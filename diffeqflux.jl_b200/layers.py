@@ -301,7 +301,7 @@ def _split_saveat(saveat, t0, t1, save_start, save_end, save_everystep):
     if save_end is None:
         save_end = bool(save_everystep or sv.size == 0 or scalar or (t1 in sv))
     lo, hi = min(t0, t1), max(t0, t1)
-    interior = np.array([s for s in sv if lo < s < hi], dtype=np.float32)
+    interior = np.sort(np.array([s for s in sv if lo < s < hi], dtype=np.float32))   # saveat is a heap upstream
     if t1 < t0:
         interior = interior[::-1].copy()
     return interior, bool(save_start), bool(save_end), bool(save_everystep) and sv.size == 0

@@ -107,6 +107,10 @@ void b200_ctx_destroy(b200_ctx* ctx);
 const char* b200_last_error(b200_ctx* ctx);
 int b200_ctx_sync(b200_ctx* ctx);
 void b200_opts_default(b200_opts* opts);
+/* Diagnostics for step-sequence parity: capacity >= 0 (re)sizes the per-ctx trace of attempted
+ * steps (0 disables, -1 leaves it); then copies up to max_entries rows (t, dt, EEst, accepted) of the
+ * LAST solve into `out` (host) and returns the number of rows. */
+int b200_ctx_trace(b200_ctx* ctx, int capacity, float* out, int max_entries);
 
 /* Chain(Dense(dims[0]=>dims[1], act[0]), ..., Dense(dims[n-1]=>dims[n], act[n-1])): the model a
  * NeuralODE / FFJORD wraps (src/neural_de.jl:35-45, src/ffjord.jl:52-73). */

@@ -115,7 +115,9 @@ def split_saveat(saveat, t0, t1, save_start=None, save_end=None, save_everystep=
     if save_end is None:
         save_end = bool(save_everystep or sv.size == 0 or scalar or (t1 in sv))
     lo, hi = min(t0, t1), max(t0, t1)
-    interior = np.array([s for s in sv if lo < s < hi], dtype=np.float32)
+    interior = np.sort(np.array([s for s in sv if lo < s < hi], dtype=np.float32))
+    if t1 < t0:
+        interior = interior[::-1].copy()
     return interior, bool(save_start), bool(save_end), bool(save_everystep)
 
 
@@ -152,7 +154,7 @@ class Adjoint:
 
 
 def adjoint(problem, p, fwd: Forward, dL_du, *, sensealg=SENSE_INTERPOLATING, abstol=1e-6,
-            reltol=1e-3, maxiters=100000, record_trace=False, augment=0) -> Adjoint:
+            reltol=1e-3, maxiters=100000, record_trace=False, augment=0, dt0=None) -> Adjoint:
     """Backward solve from t1 to t0 of d(lambda)/dt = -(df/dy)^T lambda, d(mu)/dt = -(df/dp)^T lambda
     (and dy/dt = f for Backsolve) with lambda += dL/du(t_i) at every saved time t_i."""
     ts = fwd.ts
@@ -199,7 +201,7 @@ def adjoint(problem, p, fwd: Forward, dL_du, *, sensealg=SENSE_INTERPOLATING, ab
 
     sol = tsit5.solve(rhs, z0, t1, t0, abstol=abstol, reltol=reltol, saveat=(), save_start=False,
                       save_end=True, save_everystep=False, tstops=interior, on_tstop=jump,
-                      init_jump=init_jump, maxiters=maxiters, record_trace=record_trace)
+                      init_jump=init_jump, maxiters=maxiters, record_trace=record_trace, dt0=dt0)
     lam, mu = sol.u_final[0], sol.u_final[1]
     if augment:
         lam = lam[:, :NS - augment]
