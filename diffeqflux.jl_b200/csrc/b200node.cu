@@ -31,6 +31,7 @@ struct b200_ctx {
   int rank = 0, world = 1;
   Mailbox* mailbox = nullptr;     // cudaMalloc'd (IPC-exportable)
   Mailbox* peers[MAX_RANKS] = {};
+  unsigned long long solve_seq = 0;
   // diagnostics
   float* trace_dev = nullptr;
   int trace_cap = 0;
@@ -413,6 +414,10 @@ static int run_solve(b200_ctx* ctx, int flavor, SolveParams& P, int smem_bytes, 
   P.rank = ctx->rank;
   P.world = ctx->world;
   for (int r = 0; r < MAX_RANKS; ++r) P.peers[r] = ctx->peers[r];
+  ctx->solve_seq += 1;
+  P.xbase = ctx->solve_seq << 24;
+  if (ctx->world > 1 && P.mlp.ppad > XMU_CAP)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "multi-GPU adjoint supports up to %d packed parameters (model has %d)", XMU_CAP, P.mlp.ppad);
   P.trace = ctx->trace_dev;
   P.trace_cap = ctx->trace_cap;
   const size_t header = offsetof(Ctrl, partial);

@@ -54,15 +54,20 @@ struct SmemPlan {
   int total;              // floats
 };
 
-// Multi-GPU step mailbox: rank r writes {value, tag} into slot [parity][r] of every peer.
+// Multi-GPU step mailbox (CUDA-IPC mapped into every peer): rank r writes {value, tag} into slot
+// [parity][r] of every rank.  Tags are 64-bit epochs that grow monotonically over the life of the
+// context (solve sequence number << 24 | exchange index), compared with >=.
+constexpr int XMU_CAP = 1 << 20;             // packed parameters supported by the cross-rank mu exchange
 struct Mailbox {
   volatile double val[2][2][MAX_RANKS];      // [exchange parity][component][src rank]
-  volatile unsigned int tag[2][MAX_RANKS];
+  volatile unsigned long long tag[2][MAX_RANKS];
+  volatile unsigned long long xtag[2][MAX_RANKS][MAX_CTAS];   // per mu-slice (= per CTA) tags
+  float xmu[2][MAX_RANKS][2][XMU_CAP];       // [parity][src rank][quantity][packed parameter index]
 };
 
 struct Ctrl {
   unsigned int bar;
-  unsigned int xflag;        // epoch of the last published cross-rank sum
+  unsigned long long xflag;  // epoch of the last published cross-rank sum
   int abort_flag;
   int retcode;
   int naccept, nreject, nf;
@@ -121,6 +126,7 @@ struct SolveParams {
   int b_offset;
   // multi-GPU
   int rank, world;
+  unsigned long long xbase;   // solve sequence number << 24: first exchange epoch of this solve - 1
   Mailbox* peers[MAX_RANKS];
   Ctrl* ctrl;
   float* trace;      // optional [trace_cap][4] = (t, dt, EEst, accepted) per attempted step
@@ -200,6 +206,11 @@ __device__ __forceinline__ float act_d2(int a, float h) {
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ int ld_volatile_i32(const int* p) {
@@ -406,7 +417,8 @@ struct StepShared {
   int out_idx;
   float tie;
   unsigned int epoch;
-  unsigned int xepoch;
+  unsigned long long xepoch;   // last completed scalar exchange epoch
+  unsigned long long mu_xe;    // last completed mu-slice exchange epoch
   unsigned int rhs_calls;
   InterpInfo ii[8];
   double red[NWARPS][2];
@@ -526,8 +538,8 @@ struct Solver {
   // order and publishes the total to the other CTAs of this GPU.
   __device__ void cross_rank_exchange() {
     Ctrl* c = P.ctrl;
-    const unsigned int xe = ss.xepoch + 1u;
-    const unsigned int par = xe & 1u;
+    const unsigned long long xe = ss.xepoch + 1ull;
+    const unsigned int par = (unsigned int)(xe & 1ull);
     if (cta == 0) {
       if (tid < P.world) {
         Mailbox* mb = P.peers[tid];
@@ -542,7 +554,7 @@ struct Solver {
         double s0 = 0, s1 = 0;
         long long t_start = clock64();
         for (int r = 0; r < P.world; ++r) {
-          while (me->tag[par][r] != xe) {
+          while (me->tag[par][r] < xe) {
             if (ld_volatile_i32(&c->abort_flag)) break;
             if (clock64() - t_start > 40000000000LL) {
               atomicCAS(&c->retcode, 0, -5);
@@ -562,7 +574,7 @@ struct Solver {
     }
     if (tid == 0) {
       long long t_start = clock64();
-      while (ld_acquire_u32(&c->xflag) < xe) {
+      while (ld_acquire_u64(&c->xflag) < xe) {
         if (ld_volatile_i32(&c->abort_flag)) break;
         if (clock64() - t_start > 40000000000LL) {
           atomicCAS(&c->retcode, 0, -5);
@@ -1080,28 +1092,84 @@ struct Solver {
     for (int i = tid; i < P.mlp.ppad; i += NTHREADS) s[i] = 0.f;
   }
 
-  // sum over all CTAs' slabs of (c1 * X + c2 * Y) on this CTA's slice; f(j, total) -> float to add
+  // Totals over ALL trajectories (all CTAs, all ranks) of Q0 = c1*slab[wx] + c2*slab[wy] and, if
+  // wz >= 0, Q1 = slab[wz], for the packed-parameter slice this CTA owns; returns the fp64 sum of
+  // f(j, tot0, tot1).  Cross-CTA and cross-rank sums run in fp64 in a fixed order.  With several
+  // ranks the slice totals travel through the peers' mailboxes (the parameter-gradient
+  // terms of the error norm need the global sums every step).
   template <typename F>
-  __device__ double reduce_mu(int wx, float c1, int wy, float c2, F&& f) {
+  __device__ double mu_reduce(int wx, float c1, int wy, float c2, int wz, F&& f) {
     const int pp = P.mlp.ppad;
     int chunk = (pp + P.nctas - 1) / P.nctas;
     chunk = (chunk + 3) & ~3;
-    const int lo = cta * chunk, hi = min(pp, lo + chunk);
+    const int lo = min(pp, cta * chunk), hi = min(pp, lo + chunk);
     double part = 0.0;
-    for (int j = lo + tid; j < hi; j += NTHREADS) {
-      double tot = 0.0;
+    auto local = [&](int j, double& t0, double& t1) {
+      t0 = 0.0;
+      t1 = 0.0;
       for (int cidx = 0; cidx < P.nctas; ++cidx) {
-        const float* sx = P.slabs + ((long long)cidx * 4 + wx) * pp;
-        double v = (double)c1 * (double)__ldcg(sx + j);
-        if (wy >= 0) {
-          const float* sy = P.slabs + ((long long)cidx * 4 + wy) * pp;
-          v += (double)c2 * (double)__ldcg(sy + j);
-        }
-        tot += v;
+        const float* base = P.slabs + (long long)cidx * 4 * pp + j;
+        double v = (double)c1 * (double)__ldcg(base + (long long)wx * pp);
+        if (wy >= 0) v += (double)c2 * (double)__ldcg(base + (long long)wy * pp);
+        t0 += v;
+        if (wz >= 0) t1 += (double)__ldcg(base + (long long)wz * pp);
       }
-      part += (double)f(j, (float)tot);
+    };
+    if (P.world == 1) {
+      for (int j = lo + tid; j < hi; j += NTHREADS) {
+        double t0, t1;
+        local(j, t0, t1);
+        part += (double)f(j, (float)t0, (float)t1);
+      }
+      return part;
+    }
+    if (lo >= hi) return 0.0;                       // same decision on every rank (same grid)
+    const unsigned long long xe = ss.mu_xe + 1ull;
+    const unsigned int par = (unsigned int)(xe & 1ull);
+    for (int j = lo + tid; j < hi; j += NTHREADS) {
+      double t0, t1;
+      local(j, t0, t1);
+      for (int r = 0; r < P.world; ++r) {
+        Mailbox* mb = P.peers[r];
+        mb->xmu[par][P.rank][0][j] = (float)t0;
+        if (wz >= 0) mb->xmu[par][P.rank][1][j] = (float)t1;
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      for (int r = 0; r < P.world; ++r) P.peers[r]->xtag[par][P.rank][cta] = xe;
+      Mailbox* me = P.peers[P.rank];
+      long long t_start = clock64();
+      for (int r = 0; r < P.world; ++r) {
+        while (me->xtag[par][r][cta] < xe) {
+          if (ld_volatile_i32(&P.ctrl->abort_flag)) break;
+          if (clock64() - t_start > 40000000000LL) {
+            atomicCAS(&P.ctrl->retcode, 0, -5);
+            atomicExch(&P.ctrl->abort_flag, 1);
+            break;
+          }
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    const Mailbox* me = P.peers[P.rank];
+    for (int j = lo + tid; j < hi; j += NTHREADS) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int r = 0; r < P.world; ++r) {
+        t0 += (double)__ldcg(&me->xmu[par][r][0][j]);
+        if (wz >= 0) t1 += (double)__ldcg(&me->xmu[par][r][1][j]);
+      }
+      part += (double)f(j, (float)t0, (float)t1);
     }
     return part;
+  }
+  // every CTA advances the mu-exchange epoch together (call after mu_reduce, CTA-uniformly)
+  __device__ void mu_reduce_done() {
+    __syncthreads();
+    if (tid == 0 && P.world > 1) ss.mu_xe += 1ull;
+    __syncthreads();
   }
 };
 

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
     ss.step = 0; ss.first_step = 0; ss.si = 0;
     ss.ti = T::adj ? (init_jump ? P.n_ts - 2 : P.n_ts - 1) : -1;
     ss.mu_cur = 0; ss.out_idx = 0; ss.tie = 3.0e38f;
-    ss.epoch = 0u; ss.xepoch = 0u; ss.rhs_calls = 0u;
+    ss.epoch = 0u; ss.xepoch = P.xbase; ss.mu_xe = P.xbase; ss.rhs_calls = 0u;
     ss.g1 = 2; ss.aborted = 0;
   }
   __syncthreads();
@@ -113,10 +113,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
       });
       if constexpr (T::adj) {
         S.barrier_reduce(0.0, 0.0);   // all slabs written
-        p1 += S.reduce_mu(g7, 1.f, -1, 0.f, [&](int, float tot) {
+        p1 += S.mu_reduce(g7, 1.f, -1, 0.f, -1, [&](int, float tot, float) {
           const float x = tot / P.abstol;       // mu(t1) = 0  =>  sk = abstol
           return x * x;
         });
+        S.mu_reduce_done();
       }
       S.barrier_reduce(p0, p1);
       if (tid == 0) {
@@ -168,10 +169,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
         });
         if constexpr (T::adj) {
           S.barrier_reduce(0.0, 0.0);
-          p2 += S.reduce_mu(0, 1.f, g7, -1.f, [&](int, float tot) {
+          p2 += S.mu_reduce(0, 1.f, g7, -1.f, -1, [&](int, float tot, float) {
             const float x = tot / P.abstol;
             return x * x;
           });
+          S.mu_reduce_done();
         }
         S.barrier_reduce(p2, 0.0);
         if (tid == 0) {
@@ -286,28 +288,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
       S.barrier_reduce(0.0, 0.0);   // every CTA's SA / SE / G7 complete
       const float* mu = P.mu + (long long)ss.mu_cur * M.ppad;
       float* mun = P.mu + (long long)(1 - ss.mu_cur) * M.ppad;
-      // two sweeps share the slab reads: totA -> mu_new, totE -> error term
-      const int pp = M.ppad;
-      int chunk = (pp + P.nctas - 1) / P.nctas;
-      chunk = (chunk + 3) & ~3;
-      const int lo = cta * chunk, hi = min(pp, lo + chunk);
-      float a = 0.f;
-      for (int j = lo + tid; j < hi; j += NTHREADS) {
-        double dA = 0.0, dE = 0.0;      // fp64: the cross-CTA order must not add rounding noise
-        for (int c2 = 0; c2 < P.nctas; ++c2) {
-          dA += (double)__ldcg(P.slabs + ((long long)c2 * 4 + 0) * pp + j);
-          dE += (double)__ldcg(P.slabs + ((long long)c2 * 4 + 1) * pp + j);
-        }
-        const float totA = (float)dA, totE = (float)dE;
+      perr += S.mu_reduce(0, 1.f, -1, 0.f, 1, [&](int j, float totA, float totE) {
         const float m0 = mu[j];
         const float m1 = fmaf(dt, totA, m0);
         mun[j] = m1;
         const float ut = dt * totE;
         const float sk = fmaf(fmaxf(fabsf(m0), fabsf(m1)), P.reltol, P.abstol);
         const float x = ut / sk;
-        a = fmaf(x, x, a);
-      }
-      perr += (double)a;
+        return x * x;
+      });
+      S.mu_reduce_done();
     }
     S.barrier_reduce(perr, 0.0);
     if (S.aborted()) break;
@@ -436,6 +426,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
 
   // ------------------------------------------------------------------ epilogue
   __syncthreads();
+  if (P.world > 1 && !S.aborted()) {
+    // closing exchange: once it completes every rank has consumed all earlier mailbox slots, so the
+    // next solve may overwrite them
+    if (tid == 0) { ss.sums[0] = 0.0; ss.sums[1] = 0.0; }
+    __syncthreads();
+    S.cross_rank_exchange();
+  }
   {
     const float* uf = S.slotv(ss.step, 0);
     const bool write_end = !T::adj && P.save_end && P.t0 != P.t1;

@@ -579,6 +579,7 @@ class FFJORD:
         o = self._solve.opts(on_dev, want_tape)
         o.seed = int(seed) & (2**64 - 1)
         o.noise_per_call = int(self.kwargs.get("noise_per_call", 1))
+        o.b_offset = _dist_state["rank"] * B            # global trajectory index of this shard (noise stream)
         if want_tape:
             o.sensealg = N.SENSE_INTERPOLATING      # hard-wired at src/ffjord.jl:143
         st = N.Stats()
@@ -783,3 +784,46 @@ def multiple_shoot(p, ode_data, tsteps, prob: ODEProblem, loss_function, *rest, 
         if i > 0:
             loss = loss + continuity_term * continuity_loss(group_predictions[i - 1][-1], u[0])
     return loss, group_predictions
+
+
+# --------------------------------------------------------------------------------------- multi-GPU plumbing
+_dist_state = {"rank": 0, "world": 1}
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous trajectory block of rank `rank`: equal shards are required
+    because every rank must launch the same grid for the in-kernel slice exchange."""
+    if n % world:
+        raise ValueError(f"batch {n} is not divisible by the {world} ranks (equal shards are required)")
+    per = n // world
+    return rank * per, (rank + 1) * per
+
+
+def gather_ipc_handles(handle: bytes, device=None) -> bytes:
+    """all_gather of the 64-byte CUDA-IPC handles over the default torch.distributed group."""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    t = torch.frombuffer(bytearray(handle), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+
+def attach_process_group(device: int = None):
+    """Wire this process's b200 context to its peers: export the step mailbox (CUDA IPC), all_gather the
+    handles, import.  Afterwards every solve on this device is one shard of a batch-sharded solve whose
+    per-step error-norm terms are exchanged inside the persistent kernel over NVLink peer memory."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None:
+        device = torch.cuda.current_device()
+    ctx = _context(device)
+    buf = C.create_string_buffer(N.IPC_HANDLE_BYTES)
+    ctx.check(N.lib().b200_ctx_ipc_export(ctx._h, buf))
+    handles = gather_ipc_handles(buf.raw, device)
+    ctx.check(N.lib().b200_ctx_ipc_import(ctx._h, rank, world, handles))
+    _dist_state.update(rank=rank, world=world)
+    dist.barrier()
+    return rank, world
