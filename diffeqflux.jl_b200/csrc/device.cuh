@@ -57,12 +57,13 @@ struct SmemPlan {
 // Multi-GPU step mailbox (CUDA-IPC mapped into every peer): rank r writes {value, tag} into slot
 // [parity][r] of every rank.  Tags are 64-bit epochs that grow monotonically over the life of the
 // context (solve sequence number << 24 | exchange index), compared with >=.
-constexpr int XMU_CAP = 1 << 20;             // packed parameters supported by the cross-rank mu exchange
+constexpr int XMU_CAP = 1 << 19;             // packed parameters supported by the cross-rank mu exchange
 struct Mailbox {
   volatile double val[2][2][MAX_RANKS];      // [exchange parity][component][src rank]
   volatile unsigned long long tag[2][MAX_RANKS];
   volatile unsigned long long xtag[2][MAX_RANKS][MAX_CTAS];   // per mu-slice (= per CTA) tags
-  float xmu[2][MAX_RANKS][2][XMU_CAP];       // [parity][src rank][quantity][packed parameter index]
+  double xmu[2][MAX_RANKS][2][XMU_CAP];      // [parity][src rank][quantity][packed parameter index], fp64 so
+                                             // that the sharded total rounds like the unsharded one
 };
 
 struct Ctrl {
@@ -1131,8 +1132,8 @@ struct Solver {
       local(j, t0, t1);
       for (int r = 0; r < P.world; ++r) {
         Mailbox* mb = P.peers[r];
-        mb->xmu[par][P.rank][0][j] = (float)t0;
-        if (wz >= 0) mb->xmu[par][P.rank][1][j] = (float)t1;
+        mb->xmu[par][P.rank][0][j] = t0;
+        if (wz >= 0) mb->xmu[par][P.rank][1][j] = t1;
       }
     }
     __threadfence_system();
@@ -1158,12 +1159,14 @@ struct Solver {
     for (int j = lo + tid; j < hi; j += NTHREADS) {
       double t0 = 0.0, t1 = 0.0;
       for (int r = 0; r < P.world; ++r) {
-        t0 += (double)__ldcg(&me->xmu[par][r][0][j]);
-        if (wz >= 0) t1 += (double)__ldcg(&me->xmu[par][r][1][j]);
+        t0 += __ldcg(&me->xmu[par][r][0][j]);
+        if (wz >= 0) t1 += __ldcg(&me->xmu[par][r][1][j]);
       }
       part += (double)f(j, (float)t0, (float)t1);
     }
-    return part;
+    // every rank evaluates the same global terms (it needs mu_new locally); only rank 0 adds them
+    // to the norm, otherwise the cross-rank sum would count them `world` times
+    return P.rank == 0 ? part : 0.0;
   }
   // every CTA advances the mu-exchange epoch together (call after mu_reduce, CTA-uniformly)
   __device__ void mu_reduce_done() {

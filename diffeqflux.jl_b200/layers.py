@@ -217,6 +217,8 @@ def _pick_device(*xs):
     for x in xs:
         if _is_torch(x) and x.is_cuda:
             return x.device.index if x.device.index is not None else torch.cuda.current_device()
+    if torch is not None and torch.cuda.is_available():
+        return torch.cuda.current_device()       # host (numpy) buffers: the process's current CUDA device
     return 0
 
 

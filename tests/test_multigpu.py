@@ -22,4 +22,5 @@ def test_two_gpu_shards_follow_the_single_gpu_step_sequence(sense):
     assert line, r.stdout[-2000:] + r.stderr[-4000:]
     for res in json.loads(line[0][len("MGPU_RESULT "):]):
         assert res["steps_sharded"] == res["steps_single"], res
-        assert res["state_err"] < 1e-5 and res["du0_err"] < 1e-4 and res["dp_err"] < 1e-4, res
+        # fp64 partial sums in a fixed order: the sharded run is bitwise the unsharded run
+        assert res["state_err"] <= 1e-6 and res["du0_err"] <= 1e-6 and res["dp_err"] <= 1e-6, res
