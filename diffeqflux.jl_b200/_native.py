@@ -36,14 +36,14 @@ class Opts(C.Structure):
                 ("maxiters", C.c_int), ("save_start", C.c_int), ("save_end", C.c_int),
                 ("sensealg", C.c_int), ("ptr_kind", C.c_int), ("tile", C.c_int),
                 ("max_dense_steps", C.c_int), ("seed", C.c_uint64), ("noise_per_call", C.c_int),
-                ("b_offset", C.c_int), ("save_everystep", C.c_int), ("reserved", C.c_int * 3)]
+                ("b_offset", C.c_int), ("save_everystep", C.c_int), ("path", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class Stats(C.Structure):
     _fields_ = [("retcode", C.c_int), ("naccept", C.c_int), ("nreject", C.c_int), ("nf", C.c_int),
                 ("t_final", C.c_float), ("dt_last", C.c_float), ("tie_dist", C.c_float),
                 ("kernel_ms", C.c_float), ("n_out", C.c_int), ("grid", C.c_int), ("tile", C.c_int),
-                ("reserved", C.c_int * 5)]
+                ("engine", C.c_int), ("reserved", C.c_int * 4)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -53,6 +53,8 @@ struct b200_tape {
   float t0 = 0, t1 = 0;
   float* wp = nullptr;
   float* wtp = nullptr;
+  uint8_t* wimg = nullptr;     // tensor-core weight image (chunk blobs)
+  TcParams tc{};
   float* ring = nullptr;
   int nslots = 0;
   long long vec_elems = 0;
@@ -268,6 +270,37 @@ __global__ void unpack_grad_kernel(MlpDesc m, const float* __restrict__ g, float
   }
 }
 
+// tensor-core weight image: layer l, K-chunk c -> [hi tile N x 128 B][lo tile], K-major SWIZZLE_128B
+__global__ void pack_tc_kernel(MlpDesc m, TcParams tc, const float* __restrict__ p, uint8_t* __restrict__ wimg) {
+  const int l = blockIdx.y;
+  const int K = m.dims[l], N = m.dims[l + 1];
+  const unsigned int unit_bytes = 2u * N * 64u;                   // [hi N x 64 B][lo N x 64 B]
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * (K / 4); i += gridDim.x * blockDim.x) {
+    const int n = i % N, k4 = i / N;
+    const int unit = k4 >> 2, kk = (k4 & 3) * 4;                  // 16 inputs per unit
+    float4 h, lo;
+    const float* w = p + m.fw_off[l] + (size_t)(16 * unit + kk) * N + n;
+    b200tc::split_tf32(w[0], h.x, lo.x);
+    b200tc::split_tf32(w[N], h.y, lo.y);
+    b200tc::split_tf32(w[2 * N], h.z, lo.z);
+    b200tc::split_tf32(w[3 * N], h.w, lo.w);
+    uint8_t* dst = wimg + tc.w_off[l] + (size_t)unit * unit_bytes + b200tc::sw64_off(n, kk);
+    *reinterpret_cast<float4*>(dst) = h;
+    *reinterpret_cast<float4*>(dst + N * 64) = lo;
+  }
+}
+
+// shapes the tcgen05 engine handles: K dims multiples of 32, N dims multiples of 16 and <= 256
+static bool tc_eligible(const MlpDesc& m, int flavor) {
+  if (flavor != FL_FWD_NODE) return false;
+  if (m.pre != B200_PRE_NONE || m.nl < 1) return false;
+  for (int l = 0; l < m.nl; ++l) {
+    if (m.dims[l] % 32 || m.dims[l] > 256) return false;
+    if (m.dims[l + 1] % 16 || m.dims[l + 1] > 256) return false;
+  }
+  return true;
+}
+
 // logpx = -sum(z^2)/2 - D/2 log(2 pi) - delta_logp      (src/ffjord.jl:171-176)
 __global__ void ffjord_logpx_kernel(const float* __restrict__ zend, int B, int D, float* __restrict__ logpx) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,7 +367,22 @@ static cudaError_t occupancy_flavor(int smem_bytes, int* blocks_per_sm) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel<FL>, NTHREADS, (size_t)smem_bytes);
 }
 
+template <int FL>
+static cudaError_t launch_flavor_tc(const SolveParams& P, int smem_bytes, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel<FL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  void* args[] = {const_cast<SolveParams*>(&P)};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(solve_kernel<FL, true>), dim3(P.nctas), dim3(TC_THREADS),
+                                     args, (size_t)smem_bytes, stream);
+}
+
 static cudaError_t launch_any(int flavor, const SolveParams& P, int smem_bytes, cudaStream_t s) {
+  if (P.tc.enabled) {
+    switch (flavor) {
+      case FL_FWD_NODE: return launch_flavor_tc<FL_FWD_NODE>(P, smem_bytes, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (flavor) {
     case FL_FWD_NODE: return launch_flavor<FL_FWD_NODE>(P, smem_bytes, s);
     case FL_FWD_FFJORD: return launch_flavor<FL_FWD_FFJORD>(P, smem_bytes, s);
@@ -405,6 +453,7 @@ static void fill_stats(b200_ctx* ctx, const SolveParams& P, float ms, b200_stats
   st->n_out = c->n_out;
   st->grid = P.nctas;
   st->tile = P.TB;
+  st->engine = P.tc.enabled;
 }
 
 // run the persistent kernel, bring the control header back
@@ -465,7 +514,7 @@ extern "C" void b200_tape_free(b200_tape* t) {
   if (!t) return;
   b200_ctx* ctx = t->ctx;
   cudaSetDevice(ctx->device);
-  dfree(ctx, t->wp); dfree(ctx, t->wtp); dfree(ctx, t->ring); dfree(ctx, t->k1_first);
+  dfree(ctx, t->wp); dfree(ctx, t->wtp); dfree(ctx, t->wimg); dfree(ctx, t->ring); dfree(ctx, t->k1_first);
   dfree(ctx, t->step_t); dfree(ctx, t->out_u); dfree(ctx, t->out_t); dfree(ctx, t->final_state);
   delete t;
 }
@@ -511,7 +560,27 @@ static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, cons
   auto fail = [&](int code) { b200_tape_free(t); return code; };
 
   P.mlp = m;
-  if ((rc = plan_tiles(ctx, m, flavor, B, o->tile, P, &smem_bytes)) != 0) return fail(rc);
+  const bool want_tc = o->path != 1 && tc_eligible(m, flavor) && (o->path == 2 || B >= 64);
+  if (o->path == 2 && !want_tc)
+    return fail(set_err(ctx, B200_ERR_UNSUPPORTED, "opts.path = 2: model shape / flavour is not eligible for the tcgen05 engine"));
+  if (want_tc) {
+    memset(&P.sp, 0, sizeof P.sp);
+    P.TB = TC_ROWS;
+    P.ntiles = (B + TC_ROWS - 1) / TC_ROWS;
+    P.nctas = std::min({P.ntiles, ctx->num_sms, MAX_CTAS});
+    smem_bytes = TC_SMEM;
+    unsigned int off = 0;
+    for (int l = 0; l < m.nl; ++l) {
+      t->tc.w_off[l] = off;
+      off += (unsigned int)(m.dims[l] / 16) * 2u * m.dims[l + 1] * 64u;
+    }
+    t->tc.enabled = 1;
+    cudaError_t e2 = dalloc(ctx, &t->wimg, (size_t)off);
+    if (e2 != cudaSuccess) return fail(set_err(ctx, B200_ERR_CUDA, "wimg alloc: %s", cudaGetErrorString(e2)));
+    t->tc.wimg = t->wimg;
+    pack_tc_kernel<<<dim3(64, m.nl), 256, 0, ctx->stream>>>(m, t->tc, p_dev, t->wimg);
+  } else if ((rc = plan_tiles(ctx, m, flavor, B, o->tile, P, &smem_bytes)) != 0) return fail(rc);
+  P.tc = t->tc;
 
   // dense tape capacity
   int cap = 0;

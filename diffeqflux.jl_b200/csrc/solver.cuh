@@ -5,19 +5,19 @@
 
 namespace b200 {
 
-template <int FL>
-__global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constant__ SolveParams P) {
+template <int FL, bool TC = false>
+__global__ void __launch_bounds__(TC ? TC_THREADS : NTHREADS, 1) solve_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(16) float sm[];
   __shared__ StepShared ss;
   using T = Traits<FL>;
-  Solver<FL> S(P, sm, ss);
+  Solver<FL, TC> S(P, sm, ss);
   const int tid = threadIdx.x;
   const int cta = blockIdx.x;
   const MlpDesc& M = P.mlp;
   const int NV = P.NV, TB = P.TB, B = P.B;
   Ctrl* ctrl = P.ctrl;
 
-  for (int i = tid; i < P.sp.total; i += NTHREADS) sm[i] = 0.f;
+  for (int i = tid; i < P.sp.total; i += blockDim.x) sm[i] = 0.f;
   const float tdir = P.t1 >= P.t0 ? 1.f : -1.f;
   const float dtmax = fabsf(__fsub_rn(P.t1, P.t0));
   const float inv_qmax = __fdiv_rn(1.f, 10.f), inv_qmin = __fdiv_rn(1.f, 0.2f);
@@ -38,6 +38,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
     ss.g1 = 2; ss.aborted = 0;
   }
   __syncthreads();
+  if constexpr (TC) {
+    S.tc_init();
+    if (tid >= NTHREADS) {      // control warps: weight loader + MMA issuer
+      S.tc_control();
+      return;
+    }
+  }
 
   // ------------------------------------------------------------------ initial state (slot 0)
   float* U0 = S.slotv(0, 0);
@@ -69,13 +76,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
     if (tid == 0 && P.save_start) ss.out_idx = 1;
     if (P.dense && cta == 0 && tid == 0) P.step_t[0] = P.t0;
   }
-  __syncthreads();
+  S.sync();
 
   if (P.t0 != P.t1) {
     // ---------------------------------------------------------------- FSAL init
     if constexpr (T::interp) {
       if (tid == 0) S.locate(P.t0, ss.ii[0]);
-      __syncthreads();
+      S.sync();
     }
     {
       SlabOut so{T::adj ? S.slab(ss.g1) : nullptr, nullptr, 0.f, nullptr, 0.f};
@@ -84,7 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
     // ---------------------------------------------------------------- initial dt (Hairer)
     if (P.dt0_user != 0.f) {
       if (tid == 0) ss.dt = tdir * fabsf(P.dt0_user);
-      __syncthreads();
+      S.sync();
     } else {
       float* F0 = S.slotv(0, 1);
       float* F1 = S.slotv(0, 2);
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
         ss.accept = (dt0 < __fmul_rn(10.f, 1.1920929e-07f)) ? 0 : 1;
         if (!ss.accept) ss.dt = tdir * 1e-6f;
       }
-      __syncthreads();
+      S.sync();
       if (ss.accept) {
         const float dt0 = ss.q11;
         const float dt0_t = tdir * dt0;
@@ -144,10 +151,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
             U1[g] = fmaf(dt0_t, F0[g], U0[g]);
           }
         });
-        __syncthreads();
+        S.sync();
         if constexpr (T::interp) {
           if (tid == 0) S.locate(__fadd_rn(P.t0, dt0_t), ss.ii[1]);
-          __syncthreads();
+          S.sync();
         }
         {
           SlabOut so{T::adj ? S.slab(0) : nullptr, nullptr, 0.f, nullptr, 0.f};
@@ -189,16 +196,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
           const float dt = (float)fmin(fmin(100.0 * (double)dt0, dt1), (double)dtmax);
           ss.dt = tdir * dt;
         }
-        __syncthreads();
+        S.sync();
       }
       if (tid == 0) { ss.EEst = 0.f; ss.q11 = 1.f; ss.accept = 0; }
-      __syncthreads();
+      S.sync();
     }
   }
 
   // ------------------------------------------------------------------ main loop
   while (P.t0 != P.t1) {
-    __syncthreads();   // nobody still reads the previous iteration's ss fields
+    S.sync();   // nobody still reads the previous iteration's ss fields
     // ---- loop header (thread 0): tstop, dt clamps, exits
     if (tid == 0) {
       float tstop = P.t1;
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
         }
       }
     }
-    __syncthreads();
+    S.sync();
     if (ss.done || S.aborted()) break;
     const float t = ss.t, dt = ss.dt, tstop = ss.tnew;
     const int step = ss.step;
@@ -248,22 +255,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
         SA[i] = b1 * g;
         SE[i] = e1 * g;
       }
-      __syncthreads();
+      S.sync();
     }
 
     double perr = 0.0;
     bool first_tile = true;
     S.for_my_tiles([&](int tile) {
       for (int s = 2; s <= 7; ++s) {
-        S.build_stage(tile, u, kp, c_tab.a[s - 1], s - 1, dt, s == 7 ? unew : nullptr);
-        if constexpr (T::interp) S.build_y_interp(tile, ss.ii[s - 1]);
         SlabOut so{nullptr, nullptr, 0.f, nullptr, 0.f};
         if constexpr (T::adj) {
           if (s < 7) so = SlabOut{nullptr, S.slab(0), c_tab.a[6][s - 1], S.slab(1), c_tab.bt[s - 1]};
           else so = SlabOut{S.slab(g7), nullptr, 0.f, S.slab(1), c_tab.bt[6]};
         }
-        S.rhs_tile(tile, const_cast<float*>(kp[s - 1]), so, !first_tile, ss.rhs_calls + (s - 2));
-        __syncthreads();
+        S.stage_eval(tile, u, kp, c_tab.a[s - 1], s - 1, dt, s == 7 ? unew : nullptr, const_cast<float*>(kp[s - 1]),
+                     &ss.ii[s - 1], so, !first_tile, ss.rhs_calls + (s - 2));
+        S.sync();
       }
       // embedded error estimate of this tile
       const int base_row = tile * TB;
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
         }
       }
     }
-    __syncthreads();
+    S.sync();
     if (ss.done) break;
     if (!ss.accept) continue;
 
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
         const float tsv = P.saveat[si];
         float w[7];
         const bool exact = (tsv == tnew);
-        if (!exact) Solver<FL>::interp_weights(__fdiv_rn(__fsub_rn(tsv, t), dt), w);
+        if (!exact) Solver<FL, TC>::interp_weights(__fdiv_rn(__fsub_rn(tsv, t), dt), w);
         float* o = P.out_u + (long long)oi * B * NV;
         S.for_my_tiles([&](int tile) {
           const int base_row = tile * TB;
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
         ++si;
         ++oi;
       }
-      __syncthreads();
+      S.sync();
       if (tid == 0) { ss.si = si; ss.out_idx = oi; }
       if (P.dense && cta == 0 && tid == 0) P.step_t[step + 1] = tnew;
     }
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
       ss.g1 = g7;
       ss.mu_cur = T::adj ? 1 - ss.mu_cur : 0;
     }
-    __syncthreads();
+    S.sync();
 
     if constexpr (T::adj) {
       if (tnew == tstop) {
@@ -408,13 +414,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
               else unew[g] = P.f_us[((long long)ti * B + b) * NS + (c - NS)];
             }
           });
-          __syncthreads();
+          S.sync();
           if (tid == 0) ss.ti = ti - 1;
-          __syncthreads();
+          S.sync();
           if (!is_final) {   // FSAL re-evaluated lazily: only if the integration continues
             if constexpr (T::interp) {
               if (tid == 0) S.locate(tnew, ss.ii[0]);
-              __syncthreads();
+              S.sync();
             }
             SlabOut so{S.slab(ss.g1), nullptr, 0.f, nullptr, 0.f};
             S.eval_rhs_vec(unew, S.k1ptr_w(ss.step), &ss.ii[0], so);
@@ -425,12 +431,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
   }
 
   // ------------------------------------------------------------------ epilogue
-  __syncthreads();
+  S.sync();
   if (P.world > 1 && !S.aborted()) {
     // closing exchange: once it completes every rank has consumed all earlier mailbox slots, so the
     // next solve may overwrite them
     if (tid == 0) { ss.sums[0] = 0.0; ss.sums[1] = 0.0; }
-    __syncthreads();
+    S.sync();
     S.cross_rank_exchange();
   }
   {
@@ -470,6 +476,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_kernel(const __grid_constan
       ctrl->n_out = n_out;
     }
   }
+  if constexpr (TC) S.tc_fini();
 }
 
 }  // namespace b200

@@ -36,15 +36,16 @@ Base.@kwdef mutable struct B200Opts
     noise_per_call::Cint = 1
     b_offset::Cint = 0
     save_everystep::Cint = 0
-    reserved::NTuple{3, Cint} = (0, 0, 0)
+    path::Cint = 0              # 0 auto, 1 FFMA only, 2 require tcgen05
+    reserved::NTuple{2, Cint} = (0, 0)
 end
 
 mutable struct B200Stats
     retcode::Cint; naccept::Cint; nreject::Cint; nf::Cint
     t_final::Cfloat; dt_last::Cfloat; tie_dist::Cfloat; kernel_ms::Cfloat
-    n_out::Cint; grid::Cint; tile::Cint
-    reserved::NTuple{5, Cint}
-    B200Stats() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, (0, 0, 0, 0, 0))
+    n_out::Cint; grid::Cint; tile::Cint; engine::Cint
+    reserved::NTuple{4, Cint}
+    B200Stats() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, (0, 0, 0, 0))
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)

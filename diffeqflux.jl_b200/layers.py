@@ -243,6 +243,7 @@ class SolveStats:
     tie_dist: float = float("inf")
     grid: int = 0
     tile: int = 0
+    engine: int = 0
 
 
 class ODESolution:
@@ -279,7 +280,7 @@ def Array(sol: ODESolution):
 
 
 _SOLVE_KW = {"saveat", "abstol", "reltol", "save_everystep", "save_start", "save_end", "sensealg",
-             "dt", "maxiters", "tile", "max_dense_steps", "dense"}
+             "dt", "maxiters", "tile", "max_dense_steps", "dense", "path"}
 
 
 def _split_saveat(saveat, t0, t1, save_start, save_end, save_everystep):
@@ -338,6 +339,7 @@ class _Solve:
         o.maxiters = int(self.kw.get("maxiters", 100000))
         o.tile = int(self.kw.get("tile", 0))
         o.max_dense_steps = int(self.kw.get("max_dense_steps", 0))
+        o.path = int(self.kw.get("path", 0))
         o.ptr_kind = N.PTR_DEVICE if on_device else N.PTR_HOST
         o.sensealg = self.sense if want_tape else N.SENSE_NONE
         return o
@@ -389,7 +391,7 @@ class _Solve:
             if not want_tape:
                 N.lib().b200_tape_free(tape)
                 tape = C.c_void_p()
-        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile)
+        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile, st.engine)
         return dict(ctx=ctx, mh=mh, tape=tape, out_u=out_u, out_t=out_t, rc=rc, stats=stats, vec=vec,
                     B=B, D=D, d_in=d_in, on_dev=on_dev, dev=dev, opts=o)
 
@@ -403,7 +405,7 @@ class _Solve:
         st = N.Stats()
         rc = ctx.check(N.lib().b200_node_adjoint(ctx._h, fw["mh"], fw["tape"], dLb.ptr, C.byref(o), _ptr(du0),
                                                  _ptr(dp), C.byref(st)))
-        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile)
+        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile, st.engine)
         if fw["vec"]:
             du0 = du0[0]
         return du0, dp, rc, stats
@@ -592,7 +594,7 @@ class FFJORD:
         rc = ctx.check(N.lib().b200_ffjord_forward(ctx._h, mh, pb.ptr, xb.ptr, B, float(t0), float(t1), C.byref(o),
                                                    _ptr(logpx), _ptr(z), C.byref(st),
                                                    C.byref(tape) if want_tape else None))
-        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile)
+        stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile, st.engine)
         return dict(ctx=ctx, mh=mh, tape=tape, logpx=logpx, z=z, rc=rc, stats=stats, B=B, D=D, on_dev=on_dev,
                     dev=dev, opts=o)
 
@@ -604,7 +606,7 @@ class FFJORD:
         st = N.Stats()
         rc = ctx.check(N.lib().b200_ffjord_adjoint(ctx._h, fw["mh"], fw["tape"], gb.ptr, C.byref(o), _ptr(dx),
                                                    _ptr(dp), C.byref(st)))
-        fw["adjoint_stats"] = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile)
+        fw["adjoint_stats"] = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile, st.engine)
         fw["adjoint_rc"] = rc
         return dx, dp
 

@@ -80,7 +80,9 @@ typedef struct b200_opts {
   int b_offset;          /* global index of this shard's first trajectory (noise stream, multi-GPU) */
   int save_everystep;    /* 1: the saved points are the accepted steps (`sol.t`); needs the dense tape;
                             fetch them with b200_tape_steps (out_u/out_t of the call stay untouched) */
-  int reserved[3];
+  int path;              /* RHS engine: 0 = automatic, 1 = FP32-FFMA kernels only, 2 = require the tcgen05
+                            3xTF32 tensor-core engine (error if the model shape is not eligible) */
+  int reserved[2];
 } b200_opts;
 
 typedef struct b200_stats {
@@ -95,7 +97,8 @@ typedef struct b200_stats {
   int n_out;             /* number of saved time points written */
   int grid;              /* CTAs launched */
   int tile;              /* trajectories per tile used */
-  int reserved[5];
+  int engine;            /* 0 = FP32 FFMA, 1 = tcgen05 3xTF32 */
+  int reserved[4];
 } b200_stats;
 
 /* ---- context / model ------------------------------------------------------------------------- */

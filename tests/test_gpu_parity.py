@@ -284,3 +284,29 @@ def test_multiple_shoot():
     assert loss_inf == float("inf")
     with pytest.raises(ValueError):
         dfx.multiple_shoot(p, data, ts, prob, lambda u, uh: 0.0, dfx.Tsit5(), 1)
+
+
+@pytest.mark.parametrize("B", [200, 1000])
+def test_tensor_core_engine_forward(B):
+    """tcgen05 3xTF32 RHS engine (opts.path = 2) against the oracle and against the FP32-FFMA kernels:
+    same accepted-step sequence, states within rtol 1e-4 (observed ~5e-6)."""
+    rng, mlp, p, chain = make([64, 256, 256, 64], 3, scale=2.5)
+    u0 = rng.standard_normal((B, 64)).astype(np.float32)
+    kw = dict(abstol=1e-6, reltol=1e-6, saveat=[0.5])
+    sols = {}
+    for path in (1, 2):
+        node = dfx.NeuralODE(chain, (0.0, 1.0), dfx.Tsit5(), path=path, **kw)
+        sols[path], _ = node(u0, p, {})
+        assert sols[path].stats.engine == path - 1 and sols[path].retcode == 0
+    fw = onode.forward(onode.NodeProblem(mlp), p, u0, 0.0, 1.0, **kw)
+    for path in (1, 2):
+        check_steps(sols[path].stats, fw.stats, f"forward path {path}", True)
+        close(sols[path].array(), fw.us, what=f"states path {path}")
+    close(sols[2].array(), sols[1].array(), rtol=2e-5, what="tensor-core vs FFMA")
+
+
+def test_tensor_core_engine_rejects_ineligible_shapes():
+    rng, mlp, p, chain = make([2, 50, 2], 1)
+    node = dfx.NeuralODE(chain, (0.0, 1.0), dfx.Tsit5(), path=2, save_everystep=False)
+    with pytest.raises(dfx.B200Error):
+        node(np.zeros((4, 2), np.float32), p, {})
