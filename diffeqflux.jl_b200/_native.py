@@ -14,10 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libb200node.so")
 HEADER = os.path.join(ROOT, "include", "b200node.h")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("b200node.cu", "device.cuh", "solver.cuh")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("b200node.cu", "tc_kernels.cu", "device.cuh", "solver.cuh", "tc_common.cuh", "tc_engine.inc")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -26,8 +26,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SOURCES[0], "-o", LIB_PATH]
-    subprocess.run(cmd, check=True, cwd=os.path.join(HERE, "csrc"))
+    cwd = os.path.join(HERE, "csrc")
+    objs, procs = [], []
+    for src in SOURCES[:2]:                  # the two translation units compile in parallel
+        obj = os.path.join(HERE, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append(subprocess.Popen(cmd, cwd=cwd))
+    for pr in procs:
+        if pr.wait() != 0:
+            raise RuntimeError("nvcc failed")
+    subprocess.run([nvcc, "-shared", "-o", LIB_PATH] + objs, check=True, cwd=cwd)
     return LIB_PATH
 
 

@@ -17,6 +17,10 @@
 
 using namespace b200;
 
+// tc_kernels.cu
+cudaError_t b200_tc_init_tableau();
+cudaError_t b200_tc_launch(int flavor, const SolveParams& P, int smem_bytes, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------------
 struct b200_ctx {
   int device = 0;
@@ -53,7 +57,7 @@ struct b200_tape {
   float t0 = 0, t1 = 0;
   float* wp = nullptr;
   float* wtp = nullptr;
-  uint8_t* wimg = nullptr;     // tensor-core weight image (chunk blobs)
+  uint8_t* wimg = nullptr;     // tensor-core weight images (forward + dgrad orientation units)
   TcParams tc{};
   float* ring = nullptr;
   int nslots = 0;
@@ -142,7 +146,7 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   const Tableau tab = host_tableau();
-  if (cudaMemcpyToSymbol(c_tab, &tab, sizeof tab) != cudaSuccess) { delete ctx; return B200_ERR_CUDA; }
+  if (cudaMemcpyToSymbol(c_tab, &tab, sizeof tab) != cudaSuccess || b200_tc_init_tableau() != cudaSuccess) { delete ctx; return B200_ERR_CUDA; }
   *out = ctx;
   return 0;
 }
@@ -290,13 +294,34 @@ __global__ void pack_tc_kernel(MlpDesc m, TcParams tc, const float* __restrict__
   }
 }
 
+// dgrad orientation: layer l, unit u = 16 outputs n: [hi tile: K rows x 64 B][lo tile], rows = inputs k
+__global__ void pack_tc_t_kernel(MlpDesc m, TcParams tc, const float* __restrict__ p, uint8_t* __restrict__ wimg_t) {
+  const int l = blockIdx.y;
+  const int K = m.dims[l], N = m.dims[l + 1];
+  const unsigned int unit_bytes = 2u * K * 64u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * (N / 4); i += gridDim.x * blockDim.x) {
+    const int n4 = i % (N / 4), k = i / (N / 4);
+    const int unit = n4 >> 2, nn = (n4 & 3) * 4;
+    const float4 w = *reinterpret_cast<const float4*>(p + m.fw_off[l] + (size_t)k * N + 16 * unit + nn);
+    float4 h, lo;
+    b200tc::split_tf32(w.x, h.x, lo.x);
+    b200tc::split_tf32(w.y, h.y, lo.y);
+    b200tc::split_tf32(w.z, h.z, lo.z);
+    b200tc::split_tf32(w.w, h.w, lo.w);
+    uint8_t* dst = wimg_t + tc.t_off[l] + (size_t)unit * unit_bytes + b200tc::sw64_off(k, nn);
+    *reinterpret_cast<float4*>(dst) = h;
+    *reinterpret_cast<float4*>(dst + K * 64) = lo;
+  }
+}
+
 // shapes the tcgen05 engine handles: K dims multiples of 32, N dims multiples of 16 and <= 256
 static bool tc_eligible(const MlpDesc& m, int flavor) {
-  if (flavor != FL_FWD_NODE) return false;
-  if (m.pre != B200_PRE_NONE || m.nl < 1) return false;
+  if (flavor != FL_FWD_NODE && flavor != FL_ADJ_NODE_BACKSOLVE && flavor != FL_ADJ_NODE_INTERP) return false;
+  if (m.pre != B200_PRE_NONE || m.nl < 1 || m.nl > MAXL_TC) return false;
+  const bool adj = flavor != FL_FWD_NODE;
   for (int l = 0; l < m.nl; ++l) {
     if (m.dims[l] % 32 || m.dims[l] > 256) return false;
-    if (m.dims[l + 1] % 16 || m.dims[l + 1] > 256) return false;
+    if (m.dims[l + 1] % (adj ? 32 : 16) || m.dims[l + 1] > 256) return false;
   }
   return true;
 }
@@ -367,22 +392,8 @@ static cudaError_t occupancy_flavor(int smem_bytes, int* blocks_per_sm) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel<FL>, NTHREADS, (size_t)smem_bytes);
 }
 
-template <int FL>
-static cudaError_t launch_flavor_tc(const SolveParams& P, int smem_bytes, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(solve_kernel<FL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (e != cudaSuccess) return e;
-  void* args[] = {const_cast<SolveParams*>(&P)};
-  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(solve_kernel<FL, true>), dim3(P.nctas), dim3(TC_THREADS),
-                                     args, (size_t)smem_bytes, stream);
-}
-
 static cudaError_t launch_any(int flavor, const SolveParams& P, int smem_bytes, cudaStream_t s) {
-  if (P.tc.enabled) {
-    switch (flavor) {
-      case FL_FWD_NODE: return launch_flavor_tc<FL_FWD_NODE>(P, smem_bytes, s);
-      default: return cudaErrorInvalidValue;
-    }
-  }
+  if (P.tc.enabled) return b200_tc_launch(flavor, P, smem_bytes, s);
   switch (flavor) {
     case FL_FWD_NODE: return launch_flavor<FL_FWD_NODE>(P, smem_bytes, s);
     case FL_FWD_FFJORD: return launch_flavor<FL_FWD_FFJORD>(P, smem_bytes, s);
@@ -574,11 +585,20 @@ static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, cons
       t->tc.w_off[l] = off;
       off += (unsigned int)(m.dims[l] / 16) * 2u * m.dims[l + 1] * 64u;
     }
+    const unsigned int fwd_bytes = off;
+    const bool want_t = o->sensealg != B200_SENSE_NONE && tc_eligible(m, FL_ADJ_NODE_BACKSOLVE);
+    if (want_t)
+      for (int l = 0; l < m.nl; ++l) {
+        t->tc.t_off[l] = off - fwd_bytes;
+        off += (unsigned int)(m.dims[l + 1] / 16) * 2u * m.dims[l] * 64u;
+      }
     t->tc.enabled = 1;
     cudaError_t e2 = dalloc(ctx, &t->wimg, (size_t)off);
     if (e2 != cudaSuccess) return fail(set_err(ctx, B200_ERR_CUDA, "wimg alloc: %s", cudaGetErrorString(e2)));
     t->tc.wimg = t->wimg;
+    t->tc.wimg_t = want_t ? t->wimg + fwd_bytes : nullptr;
     pack_tc_kernel<<<dim3(64, m.nl), 256, 0, ctx->stream>>>(m, t->tc, p_dev, t->wimg);
+    if (want_t) pack_tc_t_kernel<<<dim3(64, m.nl), 256, 0, ctx->stream>>>(m, t->tc, p_dev, t->wimg + fwd_bytes);
   } else if ((rc = plan_tiles(ctx, m, flavor, B, o->tile, P, &smem_bytes)) != 0) return fail(rc);
   P.tc = t->tc;
 
@@ -717,13 +737,42 @@ static int adjoint_core(b200_ctx* ctx, b200_tape* t, int flavor, const float* dL
   SolveParams P{};
   int smem_bytes = 0, rc;
   P.mlp = m;
-  if ((rc = plan_tiles(ctx, m, flavor, t->B, o->tile, P, &smem_bytes)) != 0) return rc;
+  uint8_t* scratch = nullptr;
+  const bool want_tc = o->path != 1 && t->tc.enabled && t->tc.wimg_t && tc_eligible(m, flavor);
+  if (o->path == 2 && !want_tc)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "opts.path = 2: adjoint not eligible for the tcgen05 engine (shape, or forward ran on the FFMA path)");
+  if (want_tc) {
+    memset(&P.sp, 0, sizeof P.sp);
+    P.TB = TC_ROWS;
+    P.ntiles = (t->B + TC_ROWS - 1) / TC_ROWS;
+    P.nctas = std::min({P.ntiles, ctx->num_sms, MAX_CTAS});
+    smem_bytes = TC_SMEM;
+    P.tc = t->tc;
+    unsigned int off = 0;
+    for (int l = 0; l < m.nl; ++l) {          // a_l: columns padded to whole 128-feature groups
+      const unsigned int nc = (unsigned int)(((m.dims[l] / 32) + 3) & ~3);
+      P.tc.ncols_a[l] = (unsigned short)nc;
+      P.tc.sa_off[l] = off;
+      off += 4u * 2u * nc * 4096u;
+    }
+    for (int l = 1; l <= m.nl; ++l) {
+      const unsigned int nc = (unsigned int)(m.dims[l] / 32);
+      P.tc.ncols_d[l] = (unsigned short)nc;
+      P.tc.sd_off[l] = off;
+      off += 4u * 2u * nc * 4096u;
+    }
+    P.tc.scratch_cta = off;
+    cudaError_t e2 = dalloc(ctx, &scratch, (size_t)off * P.nctas);
+    if (e2 != cudaSuccess) return set_err(ctx, B200_ERR_CUDA, "adjoint scratch alloc: %s", cudaGetErrorString(e2));
+    cudaMemsetAsync(scratch, 0, (size_t)off * P.nctas, ctx->stream);     // padded feature columns stay zero
+    P.tc.scratch = scratch;
+  } else if ((rc = plan_tiles(ctx, m, flavor, t->B, o->tile, P, &smem_bytes)) != 0) return rc;
   const int NS = t->NS;
   const int NV = (flavor == FL_ADJ_NODE_BACKSOLVE) ? 2 * NS : NS;
   const long long vec = (long long)t->B * NV;
   float *ring = nullptr, *k1 = nullptr, *fin = nullptr, *slabs = nullptr, *mu = nullptr, *muo = nullptr, *ts_d = nullptr;
   cudaError_t e;
-  auto cleanup = [&]() { dfree(ctx, ring); dfree(ctx, k1); dfree(ctx, slabs); dfree(ctx, mu); dfree(ctx, ts_d); };
+  auto cleanup = [&]() { dfree(ctx, ring); dfree(ctx, k1); dfree(ctx, slabs); dfree(ctx, mu); dfree(ctx, ts_d); dfree(ctx, scratch); };
 #define TRY(x) if ((e = (x)) != cudaSuccess) { cleanup(); dfree(ctx, fin); dfree(ctx, muo); return set_err(ctx, B200_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e)); }
   TRY(dalloc(ctx, &ring, (size_t)2 * 7 * vec));
   TRY(dalloc(ctx, &k1, (size_t)vec));

@@ -10,10 +10,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "tc_common.cuh"
-#ifdef B200_TC_PROF
 #include <cstdio>
-#endif
+
+#include "tc_common.cuh"
 
 namespace b200 {
 
@@ -84,25 +83,52 @@ struct Ctrl {
   double partial[2][MAX_CTAS][2];
 };
 
-// Tensor-core (tcgen05 / TMEM, 3xTF32) RHS engine: weights as pre-swizzled hi/lo chunk blobs.
-//   forward orientation, layer l, K-chunk c (32 inputs): [hi tile: N rows x 128 B][lo tile], canonical
-//   K-major SWIZZLE_128B (tc_common.cuh), streamed by cp.async.bulk into the B ring.
-//   A weight "unit" is (layer, 16 inputs): [hi tile: N rows x 64 B][lo tile], K-major SWIZZLE_64B, <= 32 KB.
+// Tensor-core (tcgen05 / TMEM, 3xTF32) RHS engine.
+//   Weight "unit" = (layer, 16 reduction indices): [hi tile: rows x 64 B][lo tile], K-major SWIZZLE_64B,
+//   <= 32 KB, streamed by cp.async.bulk into a 4-deep ring.  Forward orientation: rows = outputs n,
+//   reduction over inputs k (wimg / w_off).  Dgrad orientation: rows = inputs k, reduction over outputs n
+//   (wimg_t / t_off).
+//   Adjoint scratch (per CTA, global/L2): every activation a_l and cotangent delta_l of the tile as hi/lo
+//   tf32 in the MN-major SWIZZLE_128B_BASE32B layout the weight-gradient GEMMs read:
+//   [row quarter (4)][hi|lo][32-feature column][32 rows x 128 B].
+constexpr int MAXL_TC = 4;
 struct TcParams {
   int enabled;
   const uint8_t* wimg;
-  unsigned int w_off[MAXL];     // byte offset of layer l's first unit blob
+  const uint8_t* wimg_t;
+  unsigned int w_off[MAXL_TC];     // byte offset of layer l's first forward unit
+  unsigned int t_off[MAXL_TC];     // byte offset of layer l's first dgrad unit
+  uint8_t* scratch;                // adjoint: [nctas][scratch_cta]
+  unsigned int scratch_cta;
+  unsigned int sa_off[MAXL_TC];    // a_l   (l = 0..L-1), columns padded to a multiple of 4
+  unsigned int sd_off[MAXL_TC + 1];// delta_l (l = 1..L)
+  unsigned short ncols_a[MAXL_TC];
+  unsigned short ncols_d[MAXL_TC + 1];
 };
 constexpr int TC_ROWS = 128;                 // trajectories per tile = UMMA M
 constexpr int TC_A_SLOT = 32768;             // hi (16 KB) + lo (16 KB) of a 128 x 32 A chunk
-constexpr int TC_B_SLOT = 32768;             // hi + lo of a (<=256 outputs) x 16 inputs weight unit (SWIZZLE_64B)
-constexpr int TC_NB = 4;                     // B ring depth (units) = 2 K-chunks of prefetch
+constexpr int TC_B_SLOT = 32768;             // one weight unit
+constexpr int TC_NB = 4;                     // weight ring depth (units) = 2 K-chunks of prefetch
 constexpr int TC_THREADS = NTHREADS + 64;    // 8 worker warps + MMA-issuer warp + loader warp
 constexpr int TC_SMEM = 2 * TC_A_SLOT + TC_NB * TC_B_SLOT + 1024;
-constexpr int TC_MAX_UNITS = MAXL * 8 * 2;
-struct TcUnit {
-  unsigned int off;       // byte offset in the weight image
-  unsigned int bytes;     // 2 * N * 64
+constexpr int TC_MAX_OPS = 3 * MAXL_TC * 8;
+constexpr int TC_MAX_LOADS = 2 * MAXL_TC * 16 + MAXL_TC * 12;
+constexpr int TC_MAX_BIAS = MAXL_TC * 256;
+struct TcOp {                // one GEMM chunk for the MMA issuer
+  unsigned char kind;        // 0: K-major chunk (A slot filled by the workers + 2 weight units); 1: wgrad pair
+  unsigned char first;       // first MMA overwrites the accumulator
+  unsigned char abuf, bbuf;  // wgrad operand buffers
+  unsigned short n;          // N of the MMA
+  unsigned short acc;        // accumulator column
+  unsigned char new_b, last_b, layer_end, phase_end;   // phase_end: 1 = last op of the fwd/bwd phase, 2 = last wgrad op
+};
+struct TcLoad {              // one bulk load for the loader warp
+  unsigned int off, bytes;   // first piece
+  unsigned int off2, bytes2; // second piece (wgrad A: lo tile) or 0
+  unsigned char kind;        // 0: forward weight unit, 1: dgrad weight unit, 2: wgrad A buffer, 3: wgrad B buffer
+  unsigned char buf;
+  unsigned char first_w;     // first wgrad load of an RHS: scratch must be complete, fwd/bwd MMAs done
+  unsigned char first_f;     // first weight load of an RHS: previous wgrad phase done
 };
 
 struct SolveParams {
@@ -168,7 +194,7 @@ struct Tableau {
   float bt[7];
   float r[7][4];
 };
-__constant__ Tableau c_tab;
+static __constant__ Tableau c_tab;   // one copy per translation unit (see b200node.cu / tc_kernels.cu)
 
 static inline Tableau host_tableau() {
   Tableau t{};
@@ -469,15 +495,24 @@ struct StepShared {
   InterpInfo ii[8];
   double red[NWARPS][2];
   double sums[2];
-  // tensor-core engine
-  unsigned long long a_full[2];          // mbarriers (256 arrivals): the workers filled A slot s
-  unsigned long long mma_done[2];        // mbarriers: MMAs that read A slot s have completed
+  // tensor-core engine: mbarriers
+  unsigned long long a_full[2];          // (256 arrivals) the workers filled A slot s
+  unsigned long long mma_done[2];        // MMAs that read A slot s have completed
+  unsigned long long unit_done[TC_NB];   // MMAs that read weight slot s have completed
+  unsigned long long b_full[TC_NB];      // weight unit landed in slot s
+  unsigned long long w_full[4];          // wgrad operand buffer landed (A0, A1, B0, B1)
+  unsigned long long w_done[4];          // MMAs that read that buffer have completed
+  unsigned long long w_ready;            // (256 arrivals) scratch of this RHS complete
+  unsigned long long fb_done;            // forward/backward MMAs of this RHS complete
+  unsigned long long w_all_done;         // wgrad MMAs of this RHS complete
+  unsigned long long wacc_done;          // a wgrad layer's accumulators are complete
+  unsigned long long wacc_free;          // (256 arrivals) ... and have been read
   int tc_exit;                           // workers -> control warps: the solve is over
-  unsigned long long unit_done[TC_NB];   // mbarriers: MMAs that read B slot s have completed
-  unsigned long long b_full[TC_NB];      // mbarriers: weight unit landed in B slot s
   unsigned int tmem_base;
-  int n_units;                           // units per RHS evaluation
-  TcUnit units[TC_MAX_UNITS];
+  int n_ops, n_loads;
+  TcOp ops[TC_MAX_OPS];
+  TcLoad loads[TC_MAX_LOADS];
+  float bias_acc[4][TC_MAX_BIAS];        // per TMEM quadrant partial column sums of the cotangents
 };
 
 template <int FL>
@@ -500,6 +535,7 @@ struct Solver {
   StepShared& ss;
   const int tid, cta;
   unsigned int tc_g = 0;   // running chunk counter of the tensor-core pipeline (uniform across threads)
+  unsigned int tc_wl = 0;  // wgrad layers completed so far (worker side)
 #ifdef B200_TC_PROF
   long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PF_T(i, expr) { long long t_ = clock64(); expr; pf[i] += clock64() - t_; }
@@ -1145,7 +1181,8 @@ struct Solver {
                              float dt, float* dst, float* kout, const InterpInfo* ii, const SlabOut& so,
                              bool acc_store, unsigned int call) {
     if constexpr (TC) {
-      tc_stage_eval(tile, u, kp, coef, nk, dt, dst, kout);
+      if constexpr (Traits<FL>::adj) tc_adj_stage_eval(tile, u, kp, coef, nk, dt, dst, kout, ii, so, acc_store);
+      else tc_stage_eval(tile, u, kp, coef, nk, dt, dst, kout);
     } else {
       build_stage(tile, u, kp, coef, nk, dt, dst);
       if constexpr (Traits<FL>::interp) build_y_interp(tile, *ii);
@@ -1166,274 +1203,8 @@ struct Solver {
   }
 
   // ---------------------------------------------------------------- tensor-core engine (tcgen05)
-  __device__ __forceinline__ uint8_t* tc_base() const {
-    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm) + 1023) & ~(uintptr_t)1023);
-  }
-  __device__ void tc_init() {          // all TC_THREADS threads
-    if (tid < 32) b200tc::tmem_alloc(&ss.tmem_base, 512);
-    if (tid == 0) {
-      for (int i = 0; i < 2; ++i) {
-        b200tc::mbar_init(reinterpret_cast<uint64_t*>(&ss.a_full[i]), NTHREADS);
-        b200tc::mbar_init(reinterpret_cast<uint64_t*>(&ss.mma_done[i]), 1);
-      }
-      for (int i = 0; i < TC_NB; ++i) {
-        b200tc::mbar_init(reinterpret_cast<uint64_t*>(&ss.unit_done[i]), 1);
-        b200tc::mbar_init(reinterpret_cast<uint64_t*>(&ss.b_full[i]), 1);
-      }
-      b200tc::mbar_fence_init();
-      ss.tc_exit = 0;
-      // the weight-unit sequence of one RHS evaluation (same for every evaluation)
-      const MlpDesc& M = P.mlp;
-      int nu = 0;
-      for (int l = 0; l < M.nl; ++l) {
-        const unsigned int bytes = 2u * (unsigned int)M.dims[l + 1] * 64u;
-        unsigned int off = P.tc.w_off[l];
-        for (int c = 0; c < (M.dims[l] >> 4); ++c) {
-          ss.units[nu].off = off;
-          ss.units[nu].bytes = bytes;
-          off += bytes;
-          ++nu;
-        }
-      }
-      ss.n_units = nu;
-    }
-    b200tc::tc_fence_before();
-    __syncthreads();
-    b200tc::tc_fence_after();
-  }
-  __device__ void tc_fini() {          // worker threads only
-#ifdef B200_TC_PROF
-    if (tid == 0 && cta == 0) printf("TCPROF chunks=%u slotwait=%lld input=%lld layerwait=%lld tmemld=%lld act=%lld store=%lld fence_arrive=%lld lastwait=%lld\n", tc_g, pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7]);
-#endif
-    b200tc::tc_fence_before();
-    sync();
-    if (tid == 0) {
-      *reinterpret_cast<volatile int*>(&ss.tc_exit) = 1;
-      __threadfence_block();
-    }
-    if (tid < 32) b200tc::tmem_dealloc(ss.tmem_base, 512);
-  }
-  // bounded spin: a lost completion traps instead of hanging the GPU
-  __device__ __forceinline__ void tc_wait_bar(unsigned long long* b, unsigned int parity) {
-    uint64_t* bar = reinterpret_cast<uint64_t*>(b);
-    unsigned int spins = 0;
-    while (!b200tc::mbar_try_wait(bar, parity)) {
-      if (++spins > (1u << 28)) __trap();
-    }
-  }
-  // control-warp wait: also watches the exit flag; returns false when the solve is over
-  __device__ __forceinline__ bool tc_wait_or_exit(unsigned long long* b, unsigned int parity) {
-    uint64_t* bar = reinterpret_cast<uint64_t*>(b);
-    unsigned long long spins = 0;
-    while (!b200tc::mbar_test_wait(bar, parity)) {
-      if (*reinterpret_cast<volatile int*>(&ss.tc_exit)) return false;
-      if (++spins > (1ull << 33)) __trap();
-    }
-    return true;
-  }
-  // wait until the MMAs of pipeline chunk gq have completed
-  __device__ __forceinline__ void tc_wait_chunk(unsigned int gq) { tc_wait_bar(&ss.mma_done[gq & 1u], (gq >> 1) & 1u); }
+#include "tc_engine.inc"
 
-  // ---- control warps (threads >= NTHREADS): never touch the solver state, only the rings ----------
-  __device__ void tc_control() {
-    using namespace b200tc;
-    const int w = (tid - NTHREADS) >> 5;
-    if ((tid & 31) != 0) return;
-    uint8_t* base = tc_base();
-    uint8_t* bbase = base + 2 * TC_A_SLOT;
-    const unsigned int nu = (unsigned int)ss.n_units;
-    if (w == 1) {
-      // loader: keeps the weight ring full, one cp.async.bulk per unit
-      unsigned int q = 0;
-      for (;;) {
-        const unsigned int slot = q % TC_NB;
-        if (q >= TC_NB && !tc_wait_or_exit(&ss.unit_done[slot], ((q / TC_NB) - 1u) & 1u)) break;
-        if (*reinterpret_cast<volatile int*>(&ss.tc_exit)) break;
-        const TcUnit un = ss.units[q % nu];
-        uint64_t* bf = reinterpret_cast<uint64_t*>(&ss.b_full[slot]);
-        mbar_arrive_expect_tx(bf, un.bytes);
-        bulk_g2s(bbase + slot * TC_B_SLOT, P.tc.wimg + un.off, un.bytes, bf);
-        ++q;
-      }
-      // no bulk copy may be in flight when the CTA retires
-      for (unsigned int qq = q > TC_NB ? q - TC_NB : 0u; qq < q; ++qq) tc_wait_bar(&ss.b_full[qq % TC_NB], (qq / TC_NB) & 1u);
-      return;
-    }
-    // MMA issuer
-    const MlpDesc& M = P.mlp;
-    uint64_t da_hi[2], da_lo[2], db[TC_NB];
-    for (int i = 0; i < 2; ++i) {
-      da_hi[i] = smem_desc_k_sw128(smem_u32(base + i * TC_A_SLOT));
-      da_lo[i] = smem_desc_k_sw128(smem_u32(base + i * TC_A_SLOT + 16384));
-    }
-    for (int i = 0; i < TC_NB; ++i) db[i] = smem_desc_k_sw64(smem_u32(bbase + i * TC_B_SLOT));
-    unsigned int g = 0, q = 0;
-    for (;;) {
-      for (int l = 0; l < M.nl; ++l) {
-        const int N = M.dims[l + 1], nch = M.dims[l] >> 5;
-        const uint32_t acc = ss.tmem_base + ((l & 1) ? 256u : 0u);
-        const uint32_t idesc = idesc_tf32(TC_ROWS, N);
-        const uint64_t lo_off = (uint64_t)((N * 64) >> 4);      // lo tile follows the hi tile
-        for (int c = 0; c < nch; ++c, ++g) {
-          const unsigned int as = g & 1u;
-          if (!tc_wait_or_exit(&ss.a_full[as], (g >> 1) & 1u)) return;
-          tc_fence_after();
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh, ++q) {
-            const unsigned int bs = q % TC_NB;
-            tc_wait_bar(&ss.b_full[bs], (q / TC_NB) & 1u);
-            tc_fence_after();
-            const uint64_t bh = db[bs], bl = db[bs] + lo_off;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t aadv = (uint64_t)((hh * 2 + ks) * 2), badv = (uint64_t)(ks * 2);
-              mma_tf32(acc, da_lo[as] + aadv, bh + badv, idesc, (c | hh | ks) ? 1u : 0u);
-              mma_tf32(acc, da_hi[as] + aadv, bl + badv, idesc, 1u);
-              mma_tf32(acc, da_hi[as] + aadv, bh + badv, idesc, 1u);
-            }
-            tc_commit(reinterpret_cast<uint64_t*>(&ss.unit_done[bs]));
-          }
-          tc_commit(reinterpret_cast<uint64_t*>(&ss.mma_done[as]));
-        }
-      }
-    }
-  }
-
-  // x = u + dt*sum coef_j k_j for (row r, 16 columns from col0); zeros for rows past the batch
-  __device__ __forceinline__ void tc_stage_input16(int grow, int col0, const float* u, const float* const* kp,
-                                                   const float* coef, int nk, float dt, float* dst, float (&x)[16]) {
-    if (grow >= P.B) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = 0.f;
-      return;
-    }
-    const long long g = (long long)grow * P.NV + col0;
-    const float* kq[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) kq[j] = (j < nk) ? kp[j] : u;     // registers, no local-memory pointer table
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 v = *reinterpret_cast<const float4*>(u + g + 4 * q);
-      float4 kk[6];
-#pragma unroll
-      for (int j = 0; j < 6; ++j)                                  // all loads in flight before any FMA
-        if (j < nk) kk[j] = *reinterpret_cast<const float4*>(kq[j] + g + 4 * q);
-      if (nk > 0) {
-        float4 acc = make_float4(coef[0] * kk[0].x, coef[0] * kk[0].y, coef[0] * kk[0].z, coef[0] * kk[0].w);
-#pragma unroll
-        for (int j = 1; j < 6; ++j)
-          if (j < nk) {
-            acc.x = fmaf(coef[j], kk[j].x, acc.x); acc.y = fmaf(coef[j], kk[j].y, acc.y);
-            acc.z = fmaf(coef[j], kk[j].z, acc.z); acc.w = fmaf(coef[j], kk[j].w, acc.w);
-          }
-        v.x = fmaf(dt, acc.x, v.x); v.y = fmaf(dt, acc.y, v.y);
-        v.z = fmaf(dt, acc.z, v.z); v.w = fmaf(dt, acc.w, v.w);
-      }
-      if (dst) *reinterpret_cast<float4*>(dst + g + 4 * q) = v;
-      x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-    }
-  }
-  // 16 fp32 values of (row r, k0..k0+16) -> hi/lo tf32 in the canonical K-major SW128 A slot
-  __device__ __forceinline__ void tc_store_a16(uint8_t* slot, int r, int k0, const float (&x)[16]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 h, l;
-      b200tc::split_tf32(x[4 * q + 0], h.x, l.x);
-      b200tc::split_tf32(x[4 * q + 1], h.y, l.y);
-      b200tc::split_tf32(x[4 * q + 2], h.z, l.z);
-      b200tc::split_tf32(x[4 * q + 3], h.w, l.w);
-      const uint32_t off = b200tc::sw128_off(r, k0 + 4 * q);
-      *reinterpret_cast<float4*>(slot + off) = h;
-      *reinterpret_cast<float4*>(slot + 16384 + off) = l;
-    }
-  }
-  __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-  }
-
-  // Forward NeuralODE RHS of one 128-trajectory tile on the tensor cores.  Per 32-wide K chunk: the
-  // weight blob streams into the B ring (cp.async.bulk), all threads produce the A chunk (layer 0: the
-  // stage input from global memory; hidden layers: previous accumulator TMEM -> +bias -> tanh -> hi/lo),
-  // one thread issues the 12 MMAs (3 products x 4 K-steps) that run while the next chunk is produced.
-  __device__ void tc_stage_eval(int tile, const float* u, const float* const* kp, const float* coef, int nk,
-                                float dt, float* dst, float* kout) {
-    using namespace b200tc;
-    const MlpDesc& M = P.mlp;
-    uint8_t* base = tc_base();
-    const int warp = tid >> 5, lane = tid & 31;
-    const int r = (warp & 3) * 32 + lane;          // tile row == TMEM lane
-    const int h16 = (warp >> 2) * 16;              // which 16 of a chunk's 32 columns this thread owns
-    const int grow = tile * TC_ROWS + r;
-    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-    unsigned int g = tc_g;
-    for (int l = 0; l < M.nl; ++l) {
-      const int nch = M.dims[l] >> 5;
-      const uint32_t acc_prev = ss.tmem_base + ((l & 1) ? 0u : 256u);
-      const float* bias_prev = l > 0 ? P.wp + M.b_off[l - 1] : nullptr;
-      for (int c = 0; c < nch; ++c, ++g) {
-        const unsigned int slot = g & 1u;
-        uint8_t* a_slot = base + slot * TC_A_SLOT;
-        PF_T(0, if (g >= 2u) tc_wait_chunk(g - 2u));                 // A slot free again
-        float x[16];
-        if (l == 0) {
-          PF_T(1, tc_stage_input16(grow, 32 * c + h16, u, kp, coef, nk, dt, dst, x));
-        } else {
-          PF_T(2, if (c == 0) { tc_wait_chunk(g - 1u); tc_fence_after(); });   // previous layer's accumulator complete
-          PF_T(3, tc_ld16(acc_prev + lane_addr + (uint32_t)(32 * c + h16), x));
-          const int a = M.act[l - 1];
-          PF_T(4, {
-            const float4* bp = reinterpret_cast<const float4*>(bias_prev + 32 * c + h16);
-            _Pragma("unroll") for (int q4 = 0; q4 < 4; ++q4) {
-              const float4 bq = __ldg(bp + q4);
-              x[4 * q4 + 0] = act_apply_fast(a, x[4 * q4 + 0] + bq.x);
-              x[4 * q4 + 1] = act_apply_fast(a, x[4 * q4 + 1] + bq.y);
-              x[4 * q4 + 2] = act_apply_fast(a, x[4 * q4 + 2] + bq.z);
-              x[4 * q4 + 3] = act_apply_fast(a, x[4 * q4 + 3] + bq.w);
-            }
-          });
-        }
-        PF_T(5, tc_store_a16(a_slot, r, h16, x));
-        PF_T(6, fence_proxy_async(); tc_fence_before(); mbar_arrive(reinterpret_cast<uint64_t*>(&ss.a_full[slot])));
-      }
-    }
-    // output layer: accumulator + bias -> kout
-    PF_T(7, tc_wait_chunk(g - 1u));
-    tc_fence_after();
-    {
-      const int L = M.nl, N = M.dims[L];
-      const uint32_t acc = ss.tmem_base + (((L - 1) & 1) ? 256u : 0u);
-      const float* bias = P.wp + M.b_off[L - 1];
-      const int a = M.act[L - 1];
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        float x[16];
-        tc_ld16(acc + lane_addr + (uint32_t)(c0 + h16), x);
-        if (grow < P.B) {
-          float* o = kout + (long long)grow * P.NV + c0 + h16;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 v;
-            v.x = act_apply(a, x[4 * q + 0] + __ldg(bias + c0 + h16 + 4 * q + 0));
-            v.y = act_apply(a, x[4 * q + 1] + __ldg(bias + c0 + h16 + 4 * q + 1));
-            v.z = act_apply(a, x[4 * q + 2] + __ldg(bias + c0 + h16 + 4 * q + 2));
-            v.w = act_apply(a, x[4 * q + 3] + __ldg(bias + c0 + h16 + 4 * q + 3));
-            *reinterpret_cast<float4*>(o + 4 * q) = v;
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    tc_g = g;
-  }
 
   __device__ void zero_slab(float* s) {
     for (int i = tid; i < P.mlp.ppad; i += NTHREADS) s[i] = 0.f;

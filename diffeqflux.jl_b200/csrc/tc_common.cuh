@@ -127,6 +127,21 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw64(uint32_t smem_addr) {
 __host__ __device__ __forceinline__ uint32_t sw64_off(int r, int k) {
   return (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((((k >> 2) ^ ((r >> 1) & 3)) & 3) << 4) + ((k & 3) << 2));
 }
+// MN-major tf32 operand (weight-gradient GEMMs): SWIZZLE_128B_BASE32B is the only layout the hardware takes.
+// A 32-feature column of the matrix is a stack of 128-B lines (one per K row); inside a line the 32-B unit
+// index is XORed with (row & 3); 4 rows form a 512-B atom (SBO); columns are LBO bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_mn_b32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)1u << 61;                       // SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ __forceinline__ uint32_t mn32_off(int r, int f) {
+  return (uint32_t)(r * 128 + ((((f >> 3) ^ (r & 3)) & 3) << 5) + ((f & 7) << 2));
+}
 // instruction descriptor: kind::tf32, fp32 accumulate, A and B K-major, M x N
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
