@@ -252,12 +252,13 @@ def run_gpu(args):
                        "batch_per_gpu": B, "state": 64, "w_scale": W_SCALE, "tspan": list(TSPAN), "l2_flush_between_steps": True,
                        "nf_fwd": fs.nf, "nf_adj": as_.nf, "naccept_fwd": fs.naccept, "nreject_fwd": fs.nreject,
                        "naccept_adj": as_.naccept, "nreject_adj": as_.nreject, "grid": fs.grid, "tile": fs.tile,
+                       "engine_fwd": fs.engine, "engine_adj": as_.engine,
                        "parallelism": f"batch-sharded x{world}"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                          "traffic": None, "peak_source": f"{pk_src} bf16 sustained / 2 (TF32) / 3 (3xTF32), BASELINE.md section 2",
                          "kernel_ms_per_step": k_ms / args.steps, "algorithmic_flop_per_step": flop,
                          "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak,
-                         "note": "current kernels run the RHS GEMMs on the FP32 FFMA pipe"},
+                         "engine": "tcgen05 3xTF32" if fs.engine else "fp32 ffma"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "RHS evals/s", "h2d_bytes_per_step": int(u0_h.nbytes + p_h.nbytes),
                     "d2h_bytes_per_step": int(2 * u0_h.nbytes + p_h.nbytes), "steps": e2e_steps},
