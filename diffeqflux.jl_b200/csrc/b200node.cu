@@ -777,11 +777,11 @@ static int adjoint_core(b200_ctx* ctx, b200_tape* t, int flavor, const float* dL
   TRY(dalloc(ctx, &ring, (size_t)2 * 7 * vec));
   TRY(dalloc(ctx, &k1, (size_t)vec));
   TRY(dalloc(ctx, &fin, (size_t)vec));
-  TRY(dalloc(ctx, &slabs, (size_t)P.nctas * 4 * m.ppad));
+  TRY(dalloc(ctx, &slabs, (size_t)P.nctas * NSLAB * m.ppad));
   TRY(dalloc(ctx, &mu, (size_t)2 * m.ppad));
   TRY(dalloc(ctx, &muo, (size_t)m.ppad));
   TRY(dalloc(ctx, &ts_d, t->ts.size() + 1));
-  TRY(cudaMemsetAsync(slabs, 0, (size_t)P.nctas * 4 * m.ppad * sizeof(float), ctx->stream));
+  TRY(cudaMemsetAsync(slabs, 0, (size_t)P.nctas * NSLAB * m.ppad * sizeof(float), ctx->stream));
   TRY(cudaMemsetAsync(mu, 0, (size_t)2 * m.ppad * sizeof(float), ctx->stream));
   TRY(cudaMemsetAsync(muo, 0, (size_t)m.ppad * sizeof(float), ctx->stream));
   if (!t->ts.empty()) TRY(cudaMemcpyAsync(ts_d, t->ts.data(), t->ts.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));

@@ -21,6 +21,7 @@ constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAX_CTAS = 1024;
 constexpr int MAX_RANKS = 8;
+constexpr int NSLAB = 7;   // per-CTA weight-gradient slabs: stages 2..6 (0..4) + the two FSAL slabs G1/G7 (5, 6; swapped on accept)
 
 enum Flavor : int {
   FL_FWD_NODE = 0,
@@ -565,8 +566,8 @@ struct Solver {
   __device__ __forceinline__ const float* fslotv(int slot, int v) const {
     return P.f_ring + ((long long)(slot % P.f_nslots) * 7 + v) * P.f_vec_elems;
   }
-  __device__ __forceinline__ float* slab(int which) const {   // 0 SA, 1 SE, 2/3 G1/G7 (swapped)
-    return P.slabs + ((long long)cta * 4 + which) * P.mlp.ppad;
+  __device__ __forceinline__ float* slab(int which) const {   // 0..4: G of stages 2..6, 5/6: G1 / G7 (swapped)
+    return P.slabs + ((long long)cta * NSLAB + which) * P.mlp.ppad;
   }
 
   // ---------------------------------------------------------------- barriers / reductions
@@ -1223,10 +1224,11 @@ struct Solver {
     const int lo = min(pp, cta * chunk), hi = min(pp, lo + chunk);
     double part = 0.0;
     auto local = [&](int j, double& t0, double& t1) {
+      if (wx == -2) { step_local(j, wy, wz, t0, t1); return; }   // step mode: wy = g1, wz = g7
       t0 = 0.0;
       t1 = 0.0;
       for (int cidx = 0; cidx < P.nctas; ++cidx) {
-        const float* base = P.slabs + (long long)cidx * 4 * pp + j;
+        const float* base = P.slabs + (long long)cidx * NSLAB * pp + j;
         double v = (double)c1 * (double)__ldcg(base + (long long)wx * pp);
         if (wy >= 0) v += (double)c2 * (double)__ldcg(base + (long long)wy * pp);
         t0 += v;
@@ -1284,6 +1286,27 @@ struct Solver {
     // every rank evaluates the same global terms (it needs mu_new locally); only rank 0 adds them
     // to the norm, otherwise the cross-rank sum would count them `world` times
     return P.rank == 0 ? part : 0.0;
+  }
+  // The step's two parameter-gradient combinations for slice element j, summed over all CTAs in fp64:
+  //   t0 = sum_s b_s G_s  (mu update),  t1 = sum_s btilde_s G_s  (embedded error), G_1 = slab g1, G_7 = slab g7.
+  __device__ __forceinline__ void step_local(int j, int g1, int g7, double& t0, double& t1) const {
+    const int pp = P.mlp.ppad;
+    t0 = 0.0;
+    t1 = 0.0;
+    for (int cidx = 0; cidx < P.nctas; ++cidx) {
+      const float* base = P.slabs + (long long)cidx * NSLAB * pp + j;
+      const float k1 = __ldcg(base + (long long)g1 * pp), k7 = __ldcg(base + (long long)g7 * pp);
+      float a = c_tab.a[6][0] * k1, e = c_tab.bt[0] * k1;
+#pragma unroll
+      for (int s5 = 0; s5 < 5; ++s5) {
+        const float ks = __ldcg(base + (long long)s5 * pp);
+        a = fmaf(c_tab.a[6][1 + s5], ks, a);
+        e = fmaf(c_tab.bt[1 + s5], ks, e);
+      }
+      e = fmaf(c_tab.bt[6], k7, e);
+      t0 += (double)a;
+      t1 += (double)e;
+    }
   }
   // every CTA advances the mu-exchange epoch together (call after mu_reduce, CTA-uniformly)
   __device__ void mu_reduce_done() {

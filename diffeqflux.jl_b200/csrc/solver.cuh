@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(TC ? TC_THREADS : NTHREADS, 1) solve_kernel(co
     ss.ti = T::adj ? (init_jump ? P.n_ts - 2 : P.n_ts - 1) : -1;
     ss.mu_cur = 0; ss.out_idx = 0; ss.tie = 3.0e38f;
     ss.epoch = 0u; ss.xepoch = P.xbase; ss.mu_xe = P.xbase; ss.rhs_calls = 0u;
-    ss.g1 = 2; ss.aborted = 0;
+    ss.g1 = 5; ss.aborted = 0;
   }
   __syncthreads();
   if constexpr (TC) {
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(TC ? TC_THREADS : NTHREADS, 1) solve_kernel(co
       float* F0 = S.slotv(0, 1);
       float* F1 = S.slotv(0, 2);
       float* U1 = S.slotv(1, 0);
-      const int g7 = 5 - ss.g1;
+      const int g7 = 11 - ss.g1;
       {
         SlabOut so{T::adj ? S.slab(g7) : nullptr, nullptr, 0.f, nullptr, 0.f};
         S.eval_rhs_vec(U0, F0, &ss.ii[0], so);
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(TC ? TC_THREADS : NTHREADS, 1) solve_kernel(co
     if (ss.done || S.aborted()) break;
     const float t = ss.t, dt = ss.dt, tstop = ss.tnew;
     const int step = ss.step;
-    const int g1 = ss.g1, g7 = 5 - g1;
+    const int g1 = ss.g1, g7 = 11 - g1;
 
     float* u = S.slotv(step, 0);
     float* unew = S.slotv(step + 1, 0);
@@ -245,27 +245,13 @@ __global__ void __launch_bounds__(TC ? TC_THREADS : NTHREADS, 1) solve_kernel(co
     kp[0] = S.k1ptr(step);
     for (int j = 1; j < 7; ++j) kp[j] = S.slotv(step, j);
 
-    if constexpr (T::adj) {   // SA = b1 * G1, SE = bt1 * G1
-      const float* G1 = S.slab(g1);
-      float* SA = S.slab(0);
-      float* SE = S.slab(1);
-      const float b1 = c_tab.a[6][0], e1 = c_tab.bt[0];
-      for (int i = tid; i < M.ppad; i += NTHREADS) {
-        const float g = G1[i];
-        SA[i] = b1 * g;
-        SE[i] = e1 * g;
-      }
-      S.sync();
-    }
-
     double perr = 0.0;
     bool first_tile = true;
     S.for_my_tiles([&](int tile) {
       for (int s = 2; s <= 7; ++s) {
         SlabOut so{nullptr, nullptr, 0.f, nullptr, 0.f};
         if constexpr (T::adj) {
-          if (s < 7) so = SlabOut{nullptr, S.slab(0), c_tab.a[6][s - 1], S.slab(1), c_tab.bt[s - 1]};
-          else so = SlabOut{S.slab(g7), nullptr, 0.f, S.slab(1), c_tab.bt[6]};
+          so = SlabOut{S.slab(s < 7 ? s - 2 : g7), nullptr, 0.f, nullptr, 0.f};   // G_s stored once, combined in the mu phase
         }
         S.stage_eval(tile, u, kp, c_tab.a[s - 1], s - 1, dt, s == 7 ? unew : nullptr, const_cast<float*>(kp[s - 1]),
                      &ss.ii[s - 1], so, !first_tile, ss.rhs_calls + (s - 2));
@@ -294,7 +280,7 @@ __global__ void __launch_bounds__(TC ? TC_THREADS : NTHREADS, 1) solve_kernel(co
       S.barrier_reduce(0.0, 0.0);   // every CTA's SA / SE / G7 complete
       const float* mu = P.mu + (long long)ss.mu_cur * M.ppad;
       float* mun = P.mu + (long long)(1 - ss.mu_cur) * M.ppad;
-      perr += S.mu_reduce(0, 1.f, -1, 0.f, 1, [&](int j, float totA, float totE) {
+      perr += S.mu_reduce(-2, 0.f, g1, 0.f, g7, [&](int j, float totA, float totE) {
         const float m0 = mu[j];
         const float m1 = fmaf(dt, totA, m0);
         mun[j] = m1;
