@@ -36,6 +36,9 @@ struct b200_ctx {
   Mailbox* mailbox = nullptr;     // cudaMalloc'd (IPC-exportable)
   Mailbox* peers[MAX_RANKS] = {};
   unsigned long long solve_seq = 0;
+  // workspace cache: device blocks are reused across calls (all work is stream-ordered on ctx->stream)
+  struct Block { void* ptr; size_t size; bool free; };
+  std::vector<Block> blocks;
   // diagnostics
   float* trace_dev = nullptr;
   int trace_cap = 0;
@@ -94,12 +97,40 @@ static int set_err(b200_ctx* ctx, int code, const char* fmt, ...) {
                      __FILE__, __LINE__);                                                     \
   } while (0)
 
+// Caching device allocator: best-fit reuse of blocks this context already owns, cudaMalloc otherwise.
+// Reuse without synchronisation is safe because every kernel / copy of the library runs on ctx->stream.
+static cudaError_t dalloc_bytes(b200_ctx* ctx, void** p, size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+  int best = -1;
+  for (int i = 0; i < (int)ctx->blocks.size(); ++i) {
+    const auto& b = ctx->blocks[i];
+    if (b.free && b.size >= bytes && b.size <= bytes + bytes / 4 + (1u << 20) && (best < 0 || b.size < ctx->blocks[best].size)) best = i;
+  }
+  if (best >= 0) {
+    ctx->blocks[best].free = false;
+    *p = ctx->blocks[best].ptr;
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {       // release every cached free block and retry once
+    cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    for (auto it = ctx->blocks.begin(); it != ctx->blocks.end();) {
+      if (it->free) { cudaFree(it->ptr); it = ctx->blocks.erase(it); } else ++it;
+    }
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess) ctx->blocks.push_back({*p, bytes, false});
+  return e;
+}
 template <typename Tp>
 static cudaError_t dalloc(b200_ctx* ctx, Tp** p, size_t n) {
-  return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(Tp), ctx->stream);
+  return dalloc_bytes(ctx, reinterpret_cast<void**>(p), n * sizeof(Tp));
 }
 static void dfree(b200_ctx* ctx, void* p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  for (auto& b : ctx->blocks)
+    if (b.ptr == p) { b.free = true; return; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -157,6 +188,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int r = 0; r < ctx->world; ++r)
     if (ctx->peers[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peers[r]);
+  for (auto& b : ctx->blocks) cudaFree(b.ptr);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
   if (ctx->trace_dev) cudaFree(ctx->trace_dev);
   if (ctx->ctrl_dev) cudaFree(ctx->ctrl_dev);

@@ -1291,22 +1291,41 @@ struct Solver {
   //   t0 = sum_s b_s G_s  (mu update),  t1 = sum_s btilde_s G_s  (embedded error), G_1 = slab g1, G_7 = slab g7.
   __device__ __forceinline__ void step_local(int j, int g1, int g7, double& t0, double& t1) const {
     const int pp = P.mlp.ppad;
-    t0 = 0.0;
-    t1 = 0.0;
-    for (int cidx = 0; cidx < P.nctas; ++cidx) {
+    constexpr int U = 8;                       // independent chains: 56 loads in flight per thread
+    double sa[U], se[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) sa[u] = se[u] = 0.0;
+    auto one = [&](int cidx, float& a, float& e) {
       const float* base = P.slabs + (long long)cidx * NSLAB * pp + j;
       const float k1 = __ldcg(base + (long long)g1 * pp), k7 = __ldcg(base + (long long)g7 * pp);
-      float a = c_tab.a[6][0] * k1, e = c_tab.bt[0] * k1;
+      float ks[5];
+#pragma unroll
+      for (int s5 = 0; s5 < 5; ++s5) ks[s5] = __ldcg(base + (long long)s5 * pp);
+      a = c_tab.a[6][0] * k1;
+      e = c_tab.bt[0] * k1;
 #pragma unroll
       for (int s5 = 0; s5 < 5; ++s5) {
-        const float ks = __ldcg(base + (long long)s5 * pp);
-        a = fmaf(c_tab.a[6][1 + s5], ks, a);
-        e = fmaf(c_tab.bt[1 + s5], ks, e);
+        a = fmaf(c_tab.a[6][1 + s5], ks[s5], a);
+        e = fmaf(c_tab.bt[1 + s5], ks[s5], e);
       }
       e = fmaf(c_tab.bt[6], k7, e);
-      t0 += (double)a;
-      t1 += (double)e;
+    };
+    int cidx = 0;
+    for (; cidx + U <= P.nctas; cidx += U) {
+      float a[U], e[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) one(cidx + u, a[u], e[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) { sa[u] += (double)a[u]; se[u] += (double)e[u]; }
     }
+    for (int u = 0; cidx < P.nctas; ++cidx, ++u) {
+      float a, e;
+      one(cidx, a, e);
+      sa[u] += (double)a;
+      se[u] += (double)e;
+    }
+    t0 = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
+    t1 = ((se[0] + se[1]) + (se[2] + se[3])) + ((se[4] + se[5]) + (se[6] + se[7]));
   }
   // every CTA advances the mu-exchange epoch together (call after mu_reduce, CTA-uniformly)
   __device__ void mu_reduce_done() {
