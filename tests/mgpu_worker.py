@@ -20,16 +20,18 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     rank, world = dist.get_rank(), dist.get_world_size()
     sense = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    tc = len(sys.argv) > 2 and sys.argv[2] == "tc"          # tensor-core engine shape
     rng = np.random.default_rng(3)
-    dims = [16, 64, 64, 16]
-    chain = dfx.Chain(dfx.Dense(16, 64, dfx.tanh), dfx.Dense(64, 64, dfx.tanh), dfx.Dense(64, 16))
+    dims = [64, 128, 128, 64] if tc else [16, 64, 64, 16]
+    chain = dfx.Chain(dfx.Dense(dims[0], dims[1], dfx.tanh), dfx.Dense(dims[1], dims[2], dfx.tanh), dfx.Dense(dims[2], dims[3]))
     p = np.concatenate([np.concatenate([(rng.standard_normal(i * o) * 3.0 / np.sqrt(i)), rng.standard_normal(o) * 0.3])
                         for i, o in zip(dims[:-1], dims[1:])]).astype(np.float32)
     B = 512
-    u0 = rng.standard_normal((B, 16)).astype(np.float32)
-    dL = np.cos(np.arange(B * 16, dtype=np.float32).reshape(1, B, 16) * 0.01)
+    u0 = rng.standard_normal((B, dims[0])).astype(np.float32)
+    dL = np.cos(np.arange(B * dims[0], dtype=np.float32).reshape(1, B, dims[0]) * 0.01)
     sa = dfx.BacksolveAdjoint() if sense else dfx.InterpolatingAdjoint()
-    kw = dict(abstol=1e-4, reltol=1e-4, save_everystep=False, save_start=False, sensealg=sa, tile=32)
+    kw = dict(abstol=1e-4, reltol=1e-4, save_everystep=False, save_start=False, sensealg=sa)
+    kw.update(dict(path=2) if tc else dict(tile=32))
     node = dfx.NeuralODE(chain, (0.0, 1.0), dfx.Tsit5(), **kw)
     # 1) unsharded reference run on this GPU (before attaching the peers)
     sol1, back1 = node.pullback(u0, p)
@@ -45,7 +47,7 @@ def main():
     def rel(a, b):
         return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
-    res = {"rank": rank, "steps_sharded": st, "steps_single": st1,
+    res = {"rank": rank, "engine": [sol.stats.engine, node.last["adjoint_stats"].engine], "steps_sharded": st, "steps_single": st1,
            "state_err": rel(sol.array(), sol1.array()[:, lo:hi]), "du0_err": rel(du, du1[lo:hi]), "dp_err": rel(dp, dp1)}
     out = [None] * world
     dist.all_gather_object(out, res)
