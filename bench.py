@@ -63,7 +63,10 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.start_row = [], None, index, 0
+
+    def mark(self):
+        self.start_row = max(0, len(self.rows) - 1)
 
     def start(self):
         try:
@@ -79,7 +82,10 @@ class ClockSampler:
 
     def stop(self):
         if self.proc:
+            time.sleep(0.12)                  # let the last sample of the timed region land
             self.proc.terminate()
+        rows = self.rows[self.start_row:] or self.rows
+        self.rows = rows
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         reasons = set()
         for r in self.rows:
@@ -191,12 +197,14 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        fs, as_, _ = step_device()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                       # nvidia-smi needs ~0.5 s to start: launch it before the warm-up
+    for _ in range(args.warmup):
+        fs, as_, _ = step_device()
     barrier()
+    if rank == 0:
+        sampler.mark()                        # only samples taken from here on count (timed region)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k_ms = 0.0
     e0.record()
