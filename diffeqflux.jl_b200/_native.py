@@ -108,7 +108,7 @@ def lib():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(os.environ.get("B200NODE_LIB") or LIB_PATH)   # the override is for kernel-variant experiments
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

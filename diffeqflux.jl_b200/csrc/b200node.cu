@@ -167,6 +167,12 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->stream = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+  if (const char* pm = getenv("B200_L2_PERSIST_MB")) {      // experiment knob: L2 set-aside for evict_last lines
+    size_t want = (size_t)atoi(pm) << 20;
+    if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    fprintf(stderr, "b200: persisting L2 set-aside %zu MB (max %d MB)\n", want >> 20, prop.persistingL2CacheMaxSize >> 20);
+  }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   cudaMalloc(&ctx->ctrl_dev, sizeof(Ctrl));
@@ -351,6 +357,7 @@ static bool tc_eligible(const MlpDesc& m, int flavor) {
   if (flavor != FL_FWD_NODE && flavor != FL_ADJ_NODE_BACKSOLVE && flavor != FL_ADJ_NODE_INTERP) return false;
   if (m.pre != B200_PRE_NONE || m.nl < 1 || m.nl > MAXL_TC) return false;
   const bool adj = flavor != FL_FWD_NODE;
+  if (adj && m.act[m.nl - 1] != ACT_ID) return false;   // the cotangent sweep seeds delta_L = lambda (identity output layer)
   for (int l = 0; l < m.nl; ++l) {
     if (m.dims[l] % 32 || m.dims[l] > 256) return false;
     if (m.dims[l + 1] % (adj ? 32 : 16) || m.dims[l + 1] > 256) return false;

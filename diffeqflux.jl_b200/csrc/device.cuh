@@ -110,7 +110,14 @@ constexpr int TC_ROWS = 128;                 // trajectories per tile = UMMA M
 constexpr int TC_A_SLOT = 32768;             // hi (16 KB) + lo (16 KB) of a 128 x 32 A chunk
 constexpr int TC_B_SLOT = 32768;             // one weight unit
 constexpr int TC_NB = 4;                     // weight ring depth (units) = 2 K-chunks of prefetch
-constexpr int TC_THREADS = NTHREADS + 64;    // 8 worker warps + MMA-issuer warp + loader warp
+#ifndef B200_TC_WORKERS
+#define B200_TC_WORKERS 256
+#endif
+constexpr int TC_WORKERS = B200_TC_WORKERS;  // epilogue/producer threads: the 256 solver threads (+ 8 helper warps)
+constexpr int TC_CW = 32 / (TC_WORKERS / 128);   // columns of a 32-wide chunk owned by one worker thread
+constexpr int TC_NQ = TC_CW / 4;
+static_assert(TC_WORKERS == 256 || TC_WORKERS == 512, "worker threads: 8 or 16 warps");
+constexpr int TC_THREADS = TC_WORKERS + 64;  // worker warps + MMA-issuer warp + loader warp (warps 8 and 9)
 constexpr int TC_SMEM = 2 * TC_A_SLOT + TC_NB * TC_B_SLOT + 1024;
 constexpr int TC_MAX_OPS = 3 * MAXL_TC * 8;
 constexpr int TC_MAX_LOADS = 2 * MAXL_TC * 16 + MAXL_TC * 12;
@@ -474,6 +481,24 @@ struct InterpInfo {
   float w[7];
 };
 
+struct SlabOut {       // what a wgrad tile does with G (already signed)
+  float* store;        // G -> store (plain)
+  float* accA; float ca;
+  float* accE; float ce;
+};
+
+struct TcArgs {        // one stage evaluation, posted by thread 0 for the helper worker warps
+  const float* u;
+  const float* kp[6];
+  float coef[6];
+  float* dst;
+  float* kout;
+  SlabOut so;
+  InterpInfo ii;
+  float dt;
+  int tile, nk, acc_store, cmd;   // cmd: 1 = evaluate, 2 = exit
+};
+
 struct StepShared {
   float t, dt, tnew;
   float qold, q11;
@@ -497,18 +522,19 @@ struct StepShared {
   double red[NWARPS][2];
   double sums[2];
   // tensor-core engine: mbarriers
-  unsigned long long a_full[2];          // (256 arrivals) the workers filled A slot s
+  unsigned long long a_full[2];          // (TC_WORKERS arrivals) the workers filled A slot s
   unsigned long long mma_done[2];        // MMAs that read A slot s have completed
   unsigned long long unit_done[TC_NB];   // MMAs that read weight slot s have completed
   unsigned long long b_full[TC_NB];      // weight unit landed in slot s
   unsigned long long w_full[4];          // wgrad operand buffer landed (A0, A1, B0, B1)
   unsigned long long w_done[4];          // MMAs that read that buffer have completed
-  unsigned long long w_ready;            // (256 arrivals) scratch of this RHS complete
+  unsigned long long w_ready;            // (TC_WORKERS arrivals) scratch of this RHS complete
   unsigned long long fb_done;            // forward/backward MMAs of this RHS complete
   unsigned long long w_all_done;         // wgrad MMAs of this RHS complete
   unsigned long long wacc_done;          // a wgrad layer's accumulators are complete
-  unsigned long long wacc_free;          // (256 arrivals) ... and have been read
+  unsigned long long wacc_free;          // (TC_WORKERS arrivals) ... and have been read
   int tc_exit;                           // workers -> control warps: the solve is over
+  TcArgs targs;
   unsigned int tmem_base;
   int n_ops, n_loads;
   TcOp ops[TC_MAX_OPS];
@@ -521,12 +547,6 @@ struct Traits {
   static constexpr bool adj = (FL >= FL_ADJ_NODE_INTERP);
   static constexpr bool interp = (FL == FL_ADJ_NODE_INTERP || FL == FL_ADJ_FFJORD);
   static constexpr bool ffjord = (FL == FL_FWD_FFJORD || FL == FL_ADJ_FFJORD);
-};
-
-struct SlabOut {       // what a wgrad tile does with G (already signed)
-  float* store;        // G -> store (plain)
-  float* accA; float ca;
-  float* accE; float ce;
 };
 
 template <int FL, bool TC = false>
@@ -1182,8 +1202,20 @@ struct Solver {
                              float dt, float* dst, float* kout, const InterpInfo* ii, const SlabOut& so,
                              bool acc_store, unsigned int call) {
     if constexpr (TC) {
+      if constexpr (TC_WORKERS > NTHREADS) {      // hand the stage to the helper warps
+        if (tid == 0) {
+          TcArgs& a = ss.targs;
+          a.u = u; a.dst = dst; a.kout = kout; a.so = so; a.dt = dt;
+          a.tile = tile; a.nk = nk; a.acc_store = acc_store ? 1 : 0; a.cmd = 1;
+          for (int j = 0; j < 6; ++j) { a.kp[j] = j < nk ? kp[j] : u; a.coef[j] = j < nk ? coef[j] : 0.f; }
+          if (ii) a.ii = *ii;
+        }
+        tc_sync_workers();
+      }
       if constexpr (Traits<FL>::adj) tc_adj_stage_eval(tile, u, kp, coef, nk, dt, dst, kout, ii, so, acc_store);
       else tc_stage_eval(tile, u, kp, coef, nk, dt, dst, kout);
+      tc_sync_workers();                          // results of every worker visible to the solver threads
+      if constexpr (Traits<FL>::adj) tc_bias_epilogue(so, acc_store);
     } else {
       build_stage(tile, u, kp, coef, nk, dt, dst);
       if constexpr (Traits<FL>::interp) build_y_interp(tile, *ii);

@@ -5,8 +5,15 @@
 
 namespace b200 {
 
+// The tensor-core translation unit (tc_kernels.cu) launches TC_THREADS threads (320, or 576 with helper warps:
+// 18 warps put 5 on one SM sub-partition of 16 K registers, which caps the kernel at 96 registers per thread).
+#ifdef B200_TC_TU
+#define B200_KERNEL_ATTR __launch_bounds__(TC_THREADS, 1)
+#else
+#define B200_KERNEL_ATTR __launch_bounds__(NTHREADS, 1)
+#endif
 template <int FL, bool TC = false>
-__global__ void __launch_bounds__(TC ? TC_THREADS : NTHREADS, 1) solve_kernel(const __grid_constant__ SolveParams P) {
+__global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(16) float sm[];
   __shared__ StepShared ss;
   using T = Traits<FL>;

@@ -1,5 +1,6 @@
 // tc_kernels.cu -- instantiations of the persistent solver with the tcgen05 RHS engine (own translation unit
 // so the two halves of the library compile in parallel).
+#define B200_TC_TU 1
 #include "solver.cuh"
 
 using namespace b200;
