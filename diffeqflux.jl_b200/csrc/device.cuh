@@ -532,6 +532,8 @@ struct StepShared {
   unsigned long long fb_done;            // forward/backward MMAs of this RHS complete
   unsigned long long w_all_done;         // wgrad MMAs of this RHS complete
   unsigned long long wacc_done;          // a wgrad layer's accumulators are complete
+  unsigned long long mu_full[2];         // mu phase: slab slices staged in the operand buffers landed
+  unsigned long long rhs_go;             // (TC_WORKERS arrivals) a new RHS evaluation starts: the loader may fetch its first units
   unsigned long long wacc_free;          // (TC_WORKERS arrivals) ... and have been read
   int tc_exit;                           // workers -> control warps: the solve is over
   TcArgs targs;
@@ -1267,26 +1269,43 @@ struct Solver {
         if (wz >= 0) t1 += (double)__ldcg(base + (long long)wz * pp);
       }
     };
-    if (P.world == 1) {
+    // every slice element this thread owns, with its two cross-CTA totals
+    auto produce = [&](auto&& sink) {
+      if constexpr (TC && Traits<FL>::adj) {
+        if (wx == -2) {                               // step mode: slabs staged through shared memory by bulk copies
+          for (int slo = lo; slo < hi; slo += MU_SUB) {
+            const int n = min(MU_SUB, hi - slo);
+            double T0[MU_SUB / NTHREADS], T1[MU_SUB / NTHREADS];
+            step_staged(slo, n, wy, wz, T0, T1);
+#pragma unroll
+            for (int k = 0; k < MU_SUB / NTHREADS; ++k) {
+              const int jj = tid + k * NTHREADS;
+              if (jj < n) sink(slo + jj, T0[k], T1[k]);
+            }
+          }
+          return;
+        }
+      }
       for (int j = lo + tid; j < hi; j += NTHREADS) {
         double t0, t1;
         local(j, t0, t1);
-        part += (double)f(j, (float)t0, (float)t1);
+        sink(j, t0, t1);
       }
+    };
+    if (P.world == 1) {
+      produce([&](int j, double t0, double t1) { part += (double)f(j, (float)t0, (float)t1); });
       return part;
     }
     if (lo >= hi) return 0.0;                       // same decision on every rank (same grid)
     const unsigned long long xe = ss.mu_xe + 1ull;
     const unsigned int par = (unsigned int)(xe & 1ull);
-    for (int j = lo + tid; j < hi; j += NTHREADS) {
-      double t0, t1;
-      local(j, t0, t1);
+    produce([&](int j, double t0, double t1) {
       for (int r = 0; r < P.world; ++r) {
         Mailbox* mb = P.peers[r];
         mb->xmu[par][P.rank][0][j] = t0;
         if (wz >= 0) mb->xmu[par][P.rank][1][j] = t1;
       }
-    }
+    });
     __threadfence_system();
     sync();
     if (tid == 0) {
@@ -1358,6 +1377,62 @@ struct Solver {
     }
     t0 = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
     t1 = ((se[0] + se[1]) + (se[2] + se[3])) + ((se[4] + se[5]) + (se[6] + se[7]));
+  }
+  // Tensor-core adjoint kernels: the same totals for slice elements [slo, slo + n), n <= MU_SUB, with the slab
+  // slices of MU_CB CTAs at a time staged in the (idle) operand buffers by cp.async.bulk -- the copy engine
+  // keeps ~170 KB in flight per SM where register-held loads reach ~30 GB/s per SM.  Thread t gets elements
+  // slo + t + k*NTHREADS.  Sums over CTAs run in fp64 in CTA order (deterministic).
+  static constexpr int MU_SUB = 1024, MU_CB = 3;
+  unsigned int mu_use[2] = {0u, 0u};
+  __device__ void step_staged(int slo, int n, int g1, int g7, double (&T0)[MU_SUB / NTHREADS], double (&T1)[MU_SUB / NTHREADS]) {
+    using namespace b200tc;
+    const int pp = P.mlp.ppad;
+    float* stage = reinterpret_cast<float*>(tc_base());
+    constexpr int BUF = MU_CB * NSLAB * MU_SUB;       // floats per staging buffer
+    const int nb = (P.nctas + MU_CB - 1) / MU_CB;
+    auto issue = [&](int b) {                         // one thread
+      const int buf = b & 1, c0 = b * MU_CB, cn = min(MU_CB, P.nctas - c0);
+      uint64_t* bar = reinterpret_cast<uint64_t*>(&ss.mu_full[buf]);
+      mbar_arrive_expect_tx(bar, (uint32_t)(cn * NSLAB * n * 4));
+      for (int c = 0; c < cn; ++c)
+        for (int sl = 0; sl < NSLAB; ++sl)
+          bulk_g2s(stage + buf * BUF + (c * NSLAB + sl) * MU_SUB, P.slabs + ((long long)(c0 + c) * NSLAB + sl) * pp + slo,
+                   (uint32_t)(n * 4), bar);
+    };
+    if (tid == 0) {
+      issue(0);
+      if (nb > 1) issue(1);
+    }
+#pragma unroll
+    for (int k = 0; k < MU_SUB / NTHREADS; ++k) T0[k] = T1[k] = 0.0;
+    for (int b = 0; b < nb; ++b) {
+      const int buf = b & 1, cn = min(MU_CB, P.nctas - b * MU_CB);
+      tc_wait_bar(&ss.mu_full[buf], mu_use[buf] & 1u);
+      mu_use[buf] += 1u;
+      const float* sb = stage + buf * BUF;
+      for (int c = 0; c < cn; ++c) {
+#pragma unroll
+        for (int k = 0; k < MU_SUB / NTHREADS; ++k) {
+          const int jj = tid + k * NTHREADS;
+          if (jj < n) {
+            const float* q = sb + c * NSLAB * MU_SUB + jj;
+            const float k1 = q[g1 * MU_SUB], k7 = q[g7 * MU_SUB];
+            float a = c_tab.a[6][0] * k1, e = c_tab.bt[0] * k1;
+#pragma unroll
+            for (int s5 = 0; s5 < 5; ++s5) {
+              const float ks = q[s5 * MU_SUB];
+              a = fmaf(c_tab.a[6][1 + s5], ks, a);
+              e = fmaf(c_tab.bt[1 + s5], ks, e);
+            }
+            e = fmaf(c_tab.bt[6], k7, e);
+            T0[k] += (double)a;
+            T1[k] += (double)e;
+          }
+        }
+      }
+      sync();                                         // buffer drained by every thread
+      if (tid == 0 && b + 2 < nb) issue(b + 2);
+    }
   }
   // every CTA advances the mu-exchange epoch together (call after mu_reduce, CTA-uniformly)
   __device__ void mu_reduce_done() {

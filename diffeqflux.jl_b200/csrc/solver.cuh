@@ -53,6 +53,10 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
     }
   }
 
+#ifdef B200_TC_PROF
+  long long qf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long qf_start = clock64();
+#endif
   // ------------------------------------------------------------------ initial state (slot 0)
   float* U0 = S.slotv(0, 0);
   S.for_my_tiles([&](int tile) {
@@ -254,6 +258,9 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
 
     double perr = 0.0;
     bool first_tile = true;
+#ifdef B200_TC_PROF
+    long long q_t0 = clock64();
+#endif
     S.for_my_tiles([&](int tile) {
       for (int s = 2; s <= 7; ++s) {
         SlabOut so{nullptr, nullptr, 0.f, nullptr, 0.f};
@@ -264,27 +271,56 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
                      &ss.ii[s - 1], so, !first_tile, ss.rhs_calls + (s - 2));
         S.sync();
       }
-      // embedded error estimate of this tile
+#ifdef B200_TC_PROF
+      qf[0] += clock64() - q_t0; q_t0 = clock64();
+#endif
+      // embedded error estimate of this tile (tile rows are contiguous in every vector; NV % 4 == 0 on the
+      // tensor-core path, so 16-byte loads there)
       const int base_row = tile * TB;
       float a = 0.f;
-      for (int e = tid; e < TB * NV; e += NTHREADS) {
-        const int r = e / NV;
-        if (base_row + r >= B) continue;
-        const long long g = (long long)base_row * NV + e;
-        float acc = c_tab.bt[0] * kp[0][g];
-#pragma unroll
-        for (int j = 1; j < 7; ++j) acc = fmaf(c_tab.bt[j], kp[j][g], acc);
+      auto err_term = [&](float k0, float k1, float k2, float k3, float k4, float k5, float k6, float uo, float un) {
+        float acc = c_tab.bt[0] * k0;
+        acc = fmaf(c_tab.bt[1], k1, acc); acc = fmaf(c_tab.bt[2], k2, acc); acc = fmaf(c_tab.bt[3], k3, acc);
+        acc = fmaf(c_tab.bt[4], k4, acc); acc = fmaf(c_tab.bt[5], k5, acc); acc = fmaf(c_tab.bt[6], k6, acc);
         const float ut = dt * acc;
-        const float sk = fmaf(fmaxf(fabsf(u[g]), fabsf(unew[g])), P.reltol, P.abstol);
+        const float sk = fmaf(fmaxf(fabsf(uo), fabsf(un)), P.reltol, P.abstol);
         const float x = ut / sk;
-        a = fmaf(x, x, a);
+        return x * x;
+      };
+      if constexpr (TC) {
+        const int rows = min(TB, B - base_row);
+        const long long g0 = (long long)base_row * NV;
+        for (int e = tid * 4; e < rows * NV; e += NTHREADS * 4) {
+          const long long g = g0 + e;
+          float4 kk[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) kk[j] = *reinterpret_cast<const float4*>(kp[j] + g);
+          const float4 uo = *reinterpret_cast<const float4*>(u + g), un = *reinterpret_cast<const float4*>(unew + g);
+          a += err_term(kk[0].x, kk[1].x, kk[2].x, kk[3].x, kk[4].x, kk[5].x, kk[6].x, uo.x, un.x);
+          a += err_term(kk[0].y, kk[1].y, kk[2].y, kk[3].y, kk[4].y, kk[5].y, kk[6].y, uo.y, un.y);
+          a += err_term(kk[0].z, kk[1].z, kk[2].z, kk[3].z, kk[4].z, kk[5].z, kk[6].z, uo.z, un.z);
+          a += err_term(kk[0].w, kk[1].w, kk[2].w, kk[3].w, kk[4].w, kk[5].w, kk[6].w, uo.w, un.w);
+        }
+      } else {
+        for (int e = tid; e < TB * NV; e += NTHREADS) {
+          const int r = e / NV;
+          if (base_row + r >= B) continue;
+          const long long g = (long long)base_row * NV + e;
+          a += err_term(kp[0][g], kp[1][g], kp[2][g], kp[3][g], kp[4][g], kp[5][g], kp[6][g], u[g], unew[g]);
+        }
       }
       perr += (double)a;
       first_tile = false;
     });
 
+#ifdef B200_TC_PROF
+    qf[1] += clock64() - q_t0; q_t0 = clock64();
+#endif
     if constexpr (T::adj) {
       S.barrier_reduce(0.0, 0.0);   // every CTA's SA / SE / G7 complete
+#ifdef B200_TC_PROF
+      qf[2] += clock64() - q_t0; q_t0 = clock64();
+#endif
       const float* mu = P.mu + (long long)ss.mu_cur * M.ppad;
       float* mun = P.mu + (long long)(1 - ss.mu_cur) * M.ppad;
       perr += S.mu_reduce(-2, 0.f, g1, 0.f, g7, [&](int j, float totA, float totE) {
@@ -297,8 +333,15 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
         return x * x;
       });
       S.mu_reduce_done();
+#ifdef B200_TC_PROF
+      qf[3] += clock64() - q_t0; q_t0 = clock64();
+#endif
     }
     S.barrier_reduce(perr, 0.0);
+#ifdef B200_TC_PROF
+    qf[4] += clock64() - q_t0; q_t0 = clock64();
+    qf[6] += 1;
+#endif
     if (S.aborted()) break;
 
     // ---- controller (thread 0)
@@ -469,6 +512,9 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
       ctrl->n_out = n_out;
     }
   }
+#ifdef B200_TC_PROF
+  if (cta == 0 && tid == 0) printf("TCPROF loop adj=%d steps=%lld stages=%lld errpart=%lld bar1=%lld mu=%lld bar2=%lld total=%lld\n", (int)T::adj, qf[6], qf[0], qf[1], qf[2], qf[3], qf[4], clock64() - qf_start);
+#endif
   if constexpr (TC) S.tc_fini();
 }
 
