@@ -800,6 +800,10 @@ static int adjoint_core(b200_ctx* ctx, b200_tape* t, int flavor, const float* dL
       P.tc.sd_off[l] = off;
       off += 4u * 2u * nc * 4096u;
     }
+    for (int l = 1; l < m.nl; ++l) {          // act'(a_l): 16 KB per 32-feature chunk
+      P.tc.sp_off[l] = off;
+      off += (unsigned int)(m.dims[l] / 32) * 16384u;
+    }
     P.tc.scratch_cta = off;
     cudaError_t e2 = dalloc(ctx, &scratch, (size_t)off * P.nctas);
     if (e2 != cudaSuccess) return set_err(ctx, B200_ERR_CUDA, "adjoint scratch alloc: %s", cudaGetErrorString(e2));
