@@ -167,12 +167,6 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->stream = stream ? (cudaStream_t)stream : cudaStreamLegacy;
-  if (const char* pm = getenv("B200_L2_PERSIST_MB")) {      // experiment knob: L2 set-aside for evict_last lines
-    size_t want = (size_t)atoi(pm) << 20;
-    if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    fprintf(stderr, "b200: persisting L2 set-aside %zu MB (max %d MB)\n", want >> 20, prop.persistingL2CacheMaxSize >> 20);
-  }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   cudaMalloc(&ctx->ctrl_dev, sizeof(Ctrl));
