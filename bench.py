@@ -58,6 +58,11 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE adjoint solve-kernel launch at this workload (ncu --set full capture
+# of the final round-1 build, profiles/solve_kernels_r1_final_raw.csv); algorithmic bytes are ~0 (the path is tensor bound)
+ADJ_DRAM_BYTES_PER_LAUNCH = 53.497441e9 + 52.523780e9
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -263,7 +268,7 @@ def run_gpu(args):
                        "engine_fwd": fs.engine, "engine_adj": as_.engine,
                        "parallelism": f"batch-sharded x{world}"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                         "traffic": None, "peak_source": f"{pk_src} bf16 sustained / 2 (TF32) / 3 (3xTF32), BASELINE.md section 2",
+                         "traffic": ADJ_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, adjoint solve kernel (dominant), profiles/solve_kernels_r1_final_raw.csv", "peak_source": f"{pk_src} bf16 sustained / 2 (TF32) / 3 (3xTF32), BASELINE.md section 2",
                          "kernel_ms_per_step": k_ms / args.steps, "algorithmic_flop_per_step": flop,
                          "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak,
                          "engine": "tcgen05 3xTF32" if fs.engine else "fp32 ffma"},
