@@ -781,27 +781,20 @@ static int adjoint_core(b200_ctx* ctx, b200_tape* t, int flavor, const float* dL
     P.nctas = std::min({P.ntiles, ctx->num_sms, MAX_CTAS});
     smem_bytes = TC_SMEM;
     P.tc = t->tc;
-    unsigned int off = 0;
-    for (int l = 0; l < m.nl; ++l) {          // a_l: columns padded to whole 128-feature groups
-      const unsigned int nc = (unsigned int)(((m.dims[l] / 32) + 3) & ~3);
-      P.tc.ncols_a[l] = (unsigned short)nc;
+    unsigned int off = 0;                     // per-CTA fp32 stash: 16 KB per 32-feature chunk of a_l and delta_l
+    for (int l = 0; l < m.nl; ++l) {
+      P.tc.ncols_a[l] = (unsigned short)(((m.dims[l] / 32) + 3) & ~3);       // wgrad M groups of 128 features
       P.tc.sa_off[l] = off;
-      off += 4u * 2u * nc * 4096u;
+      off += (unsigned int)(m.dims[l] / 32) * 16384u;
     }
     for (int l = 1; l <= m.nl; ++l) {
-      const unsigned int nc = (unsigned int)(m.dims[l] / 32);
-      P.tc.ncols_d[l] = (unsigned short)nc;
+      P.tc.ncols_d[l] = (unsigned short)(m.dims[l] / 32);
       P.tc.sd_off[l] = off;
-      off += 4u * 2u * nc * 4096u;
-    }
-    for (int l = 1; l < m.nl; ++l) {          // act'(a_l): 16 KB per 32-feature chunk
-      P.tc.sp_off[l] = off;
       off += (unsigned int)(m.dims[l] / 32) * 16384u;
     }
     P.tc.scratch_cta = off;
     cudaError_t e2 = dalloc(ctx, &scratch, (size_t)off * P.nctas);
     if (e2 != cudaSuccess) return set_err(ctx, B200_ERR_CUDA, "adjoint scratch alloc: %s", cudaGetErrorString(e2));
-    cudaMemsetAsync(scratch, 0, (size_t)off * P.nctas, ctx->stream);     // padded feature columns stay zero
     P.tc.scratch = scratch;
   } else if ((rc = plan_tiles(ctx, m, flavor, t->B, o->tile, P, &smem_bytes)) != 0) return rc;
   const int NS = t->NS;

@@ -101,9 +101,8 @@ struct TcParams {
   unsigned int t_off[MAXL_TC];     // byte offset of layer l's first dgrad unit
   uint8_t* scratch;                // adjoint: [nctas][scratch_cta]
   unsigned int scratch_cta;
-  unsigned int sa_off[MAXL_TC];    // a_l   (l = 0..L-1), columns padded to a multiple of 4
+  unsigned int sa_off[MAXL_TC];    // a_l   (l = 0..L-1): fp32 stash, [chunk][column group][row][TC_CW] (16 KB per 32-feature chunk)
   unsigned int sd_off[MAXL_TC + 1];// delta_l (l = 1..L)
-  unsigned int sp_off[MAXL_TC];    // act'(a_l) (l = 1..L-1), fp32, [chunk][column group][row][TC_CW]: what the cotangent sweep reads
   unsigned short ncols_a[MAXL_TC];
   unsigned short ncols_d[MAXL_TC + 1];
 };
@@ -560,8 +559,9 @@ struct Solver {
   const int tid, cta;
   unsigned int tc_g = 0;   // running chunk counter of the tensor-core pipeline (uniform across threads)
   unsigned int tc_wl = 0;  // wgrad layers completed so far (worker side)
+  unsigned int tc_wused = 0u, tc_wpar = 0u;   // wgrad operand buffers A0, A1, B0, B1: ever filled / parity of the fill count (bit per buffer)
 #ifdef B200_TC_PROF
-  long long pf[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long pf[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define PF_T(i, expr) { long long t_ = clock64(); expr; pf[i] += clock64() - t_; }
 #else
 #define PF_T(i, expr) { expr; }

@@ -43,6 +43,16 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive without the release fence (which ptxas lowers to MEMBAR.ALL.CTA and which therefore also waits for every
+// global load the thread has in flight -- the software-pipelined prefetches).  Used where the data being published
+// are this thread's shared-memory stores, already ordered by fence.proxy.async ahead of the arrive.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+#ifndef B200_TC_RELEASE_ARRIVE
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
