@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <thread>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,6 +40,10 @@ struct b200_ctx {
   // workspace cache: device blocks are reused across calls (all work is stream-ordered on ctx->stream)
   struct Block { void* ptr; size_t size; bool free; };
   std::vector<Block> blocks;
+  // multiple shooting: groups are independent solves of a fraction of the GPU each; they run concurrently on
+  // sub-contexts (own stream, control block, workspace cache), one host thread per sub-context
+  std::vector<b200_ctx*> subs;
+  bool owns_stream = false;
   // diagnostics
   float* trace_dev = nullptr;
   int trace_cap = 0;
@@ -185,6 +190,8 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
 extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (b200_ctx* sub : ctx->subs) b200_ctx_destroy(sub);
+  ctx->subs.clear();
   cudaStreamSynchronize(ctx->stream);
   for (int r = 0; r < ctx->world; ++r)
     if (ctx->peers[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peers[r]);
@@ -195,6 +202,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
   if (ctx->ctrl_host) cudaFreeHost(ctx->ctrl_host);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -367,6 +375,10 @@ __global__ void ffjord_logpx_kernel(const float* __restrict__ zend, int B, int D
   float s = 0.f;
   for (int d = 0; d < D; ++d) s = fmaf(z[d], z[d], s);
   logpx[b] = -s / 2.f - (float)(D / 2.0 * 1.8378770664093453) - z[D];
+}
+__global__ void add_into_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
 }
 // cotangent of the end state from the cotangent of logpx
 __global__ void ffjord_seed_kernel(const float* __restrict__ zend, const float* __restrict__ g, int B,
@@ -980,6 +992,28 @@ extern "C" int b200_group_ranges(int datasize, int groupsize, int* first, int* l
   return g;
 }
 
+// Sub-contexts for concurrent group solves: how many 128-trajectory-tile grids of `nctas` CTAs fit on the GPU.
+static int ensure_subs(b200_ctx* ctx, int want) {
+  while ((int)ctx->subs.size() < want) {
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) break;
+    b200_ctx* sub = nullptr;
+    if (b200_ctx_create(ctx->device, st, &sub) != 0 || !sub) { cudaStreamDestroy(st); break; }
+    sub->owns_stream = true;
+    ctx->subs.push_back(sub);
+  }
+  return (int)ctx->subs.size();
+}
+static int mshoot_lanes(b200_ctx* ctx, const MlpDesc& m, int B, int G, int path) {
+  if (ctx->world > 1 || G < 2) return 1;                       // sharded solves exchange through the parent's mailbox
+  const bool tc = path != 1 && tc_eligible(m, FL_FWD_NODE) && (path == 2 || B >= 64);
+  const int rows = tc ? TC_ROWS : 64;
+  const int ctas = std::max(1, (B + rows - 1) / rows);
+  int lanes = std::min({G, 8, std::max(1, ctx->num_sms / ctas)});
+  if (const char* e = getenv("B200_MSHOOT_LANES")) lanes = std::max(1, std::min(lanes, atoi(e)));
+  return lanes <= 1 ? 1 : std::min(lanes, ensure_subs(ctx, lanes));
+}
+
 extern "C" int b200_mshoot_forward(b200_ctx* ctx, const b200_model* model, const float* p,
                                    const float* ode_data, const float* tsteps, int T, int B, int G,
                                    const int* first, const int* last, const b200_opts* o_in, float* preds,
@@ -1006,19 +1040,60 @@ extern "C" int b200_mshoot_forward(b200_ctx* ctx, const b200_model* model, const
   temps.push_back(ts_d);
   CU(cudaMemcpyAsync(ts_d, ts.data(), T * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   int worst = 0;
-  long long row = 0;
+  std::vector<long long> row0(G + 1, 0);
   for (int g = 0; g < G; ++g) {
     const int a = first[g], b = last[g];
-    if (a < 0 || b >= T || b <= a) { rc = set_err(ctx, B200_ERR_ARG, "group %d range [%d,%d]", g, a, b); break; }
-    const int len = b - a + 1;
+    if (a < 0 || b >= T || b <= a) { free_temps(ctx, temps); return set_err(ctx, B200_ERR_ARG, "group %d range [%d,%d]", g, a, b); }
+    row0[g + 1] = row0[g] + (b - a + 1);
+  }
+  auto solve_group = [&](b200_ctx* c, int g) -> int {
+    const int a = first[g], b = last[g], len = b - a + 1;
     b200_tape* t = nullptr;
-    rc = forward_core(ctx, model, FL_FWD_NODE, p_d, data_d + (long long)a * B * D, D, 0, B, ts[a], ts[b],
-                      ts_d + a + 1, len - 2, &o, stats ? stats + g : nullptr, &t);
-    if (rc < 0) break;
-    worst = std::max(worst, rc);
-    if (preds) from_device(ctx, preds + row * B * D, t->out_u, (size_t)t->n_out * B * D, o.ptr_kind);
-    row += len;
-    if (tapes && o.sensealg != B200_SENSE_NONE) tapes[g] = t; else { cudaStreamSynchronize(ctx->stream); b200_tape_free(t); }
+    int r = forward_core(c, model, FL_FWD_NODE, p_d, data_d + (long long)a * B * D, D, 0, B, ts[a], ts[b],
+                         ts_d + a + 1, len - 2, &o, stats ? stats + g : nullptr, &t);
+    if (r < 0) return r;
+    if (preds) from_device(c, preds + row0[g] * B * D, t->out_u, (size_t)t->n_out * B * D, o.ptr_kind);
+    if (tapes && o.sensealg != B200_SENSE_NONE) tapes[g] = t; else { cudaStreamSynchronize(c->stream); b200_tape_free(t); }
+    return r;
+  };
+  if (o.max_dense_steps <= 0) {
+    // the automatic dense-tape capacity takes up to half of the free memory per solve; G tapes are alive at once
+    // (and several are sized concurrently), so split that budget between the groups up front
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const double per_step = 7.0 * (double)B * D * sizeof(float);
+    const double budget = std::min(0.5 * (double)free_b / G, 24e9);
+    o.max_dense_steps = (int)std::max(16.0, std::min((double)o.maxiters, std::min(4096.0, budget / per_step)));
+  }
+  const int lanes = mshoot_lanes(ctx, m, B, G, o.path);
+  if (lanes <= 1) {
+    for (int g = 0; g < G; ++g) {
+      rc = solve_group(ctx, g);
+      if (rc < 0) break;
+      worst = std::max(worst, rc);
+    }
+  } else {
+    cudaStreamSynchronize(ctx->stream);                       // inputs staged on the parent stream
+    std::vector<int> lane_rc(lanes, 0);
+    std::vector<std::thread> th;
+    for (int k = 0; k < lanes; ++k)
+      th.emplace_back([&, k]() {
+        b200_ctx* c = ctx->subs[k];
+        cudaSetDevice(c->device);
+        int w = 0;
+        for (int g = k; g < G; g += lanes) {
+          const int r = solve_group(c, g);
+          if (r < 0) { w = r; break; }
+          w = std::max(w, r);
+        }
+        cudaStreamSynchronize(c->stream);
+        lane_rc[k] = w;
+      });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < lanes; ++k) {
+      if (lane_rc[k] < 0) { rc = lane_rc[k]; ctx->err = ctx->subs[k]->err; break; }
+      worst = std::max(worst, lane_rc[k]);
+    }
   }
   cudaStreamSynchronize(ctx->stream);
   free_temps(ctx, temps);
@@ -1042,15 +1117,16 @@ extern "C" int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_
   if (o->ptr_kind == B200_PTR_DEVICE && dp) dp_d = dp; else { CU(dalloc(ctx, &dp_d, (size_t)m.nparams)); temps.push_back(dp_d); }
   CU(cudaMemsetAsync(dp_d, 0, m.nparams * sizeof(float), ctx->stream));
   int worst = 0;
-  long long row = 0;
-  for (int g = 0; g < G; ++g) {
+  std::vector<long long> row0(G + 1, 0);
+  for (int g = 0; g < G; ++g) row0[g + 1] = row0[g] + tapes[g]->n_out;
+  // one group's adjoint on the context that owns its tape; its parameter gradient is added to dp_acc
+  auto adj_group = [&](b200_ctx* c, int g, float* dp_acc, std::vector<void*>& tmp) -> int {
     b200_tape* t = tapes[g];
     const int flavor = t->sensealg == B200_SENSE_INTERPOLATING ? FL_ADJ_NODE_INTERP : FL_ADJ_NODE_BACKSOLVE;
     float *lam = nullptr, *mu = nullptr;
-    rc = adjoint_core(ctx, t, flavor, dL_d + row * B * D, o, &lam, &mu, stats ? stats + g : nullptr);
-    if (rc < 0) break;
-    worst = std::max(worst, rc);
-    unpack_grad_kernel<<<dim3(32, m.nl), 256, 0, ctx->stream>>>(m, mu, dp_d, 1);
+    int r = adjoint_core(c, t, flavor, dL_d + row0[g] * B * D, o, &lam, &mu, stats ? stats + g : nullptr);
+    if (r < 0) return r;
+    unpack_grad_kernel<<<dim3(32, m.nl), 256, 0, c->stream>>>(m, mu, dp_acc, 1);
     if (d_data) {
       // gradient w.r.t. this group's initial condition; groups overlap by one point so the
       // caller adds it at time index first[g]: we return per-group blocks [G][B][D]
@@ -1058,16 +1134,60 @@ extern "C" int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_
       float* dst = nullptr;
       cudaError_t e = cudaSuccess;
       if (o->ptr_kind == B200_PTR_DEVICE) dst = d_data + (long long)g * B * D;
-      else { e = dalloc(ctx, &dst, (size_t)B * D); temps.push_back(dst); }
+      else { e = dalloc(c, &dst, (size_t)B * D); tmp.push_back(dst); }
       if (e == cudaSuccess) {
         const long long n = (long long)B * D;
-        extract_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lam, B, NV, D, dst, 0);
-        if (o->ptr_kind == B200_PTR_HOST) from_device(ctx, d_data + (long long)g * B * D, dst, (size_t)n, B200_PTR_HOST);
+        extract_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(lam, B, NV, D, dst, 0);
+        if (o->ptr_kind == B200_PTR_HOST) from_device(c, d_data + (long long)g * B * D, dst, (size_t)n, B200_PTR_HOST);
       }
     }
-    dfree(ctx, lam);
-    dfree(ctx, mu);
-    row += t->n_out;
+    dfree(c, lam);
+    dfree(c, mu);
+    return r;
+  };
+  std::vector<b200_ctx*> lanes;                        // distinct owners of the tapes (sub-contexts of a concurrent forward)
+  for (int g = 0; g < G; ++g)
+    if (std::find(lanes.begin(), lanes.end(), tapes[g]->ctx) == lanes.end()) lanes.push_back(tapes[g]->ctx);
+  if (lanes.size() == 1 && lanes[0] == ctx) {
+    for (int g = 0; g < G; ++g) {
+      rc = adj_group(ctx, g, dp_d, temps);
+      if (rc < 0) break;
+      worst = std::max(worst, rc);
+    }
+  } else {
+    cudaStreamSynchronize(ctx->stream);                 // dL staged and dp zeroed on the parent stream
+    const int nl = (int)lanes.size();
+    std::vector<int> lane_rc(nl, 0);
+    std::vector<float*> lane_dp(nl, nullptr);
+    std::vector<std::vector<void*>> lane_tmp(nl);
+    std::vector<std::thread> th;
+    for (int k = 0; k < nl; ++k)
+      th.emplace_back([&, k]() {
+        b200_ctx* c = lanes[k];
+        cudaSetDevice(c->device);
+        int w = 0;
+        if (dalloc(c, &lane_dp[k], (size_t)m.nparams) != cudaSuccess) { lane_rc[k] = B200_ERR_CUDA; return; }
+        cudaMemsetAsync(lane_dp[k], 0, m.nparams * sizeof(float), c->stream);
+        for (int g = 0; g < G; ++g) {
+          if (tapes[g]->ctx != c) continue;
+          const int r = adj_group(c, g, lane_dp[k], lane_tmp[k]);
+          if (r < 0) { w = r; break; }
+          w = std::max(w, r);
+        }
+        cudaStreamSynchronize(c->stream);
+        lane_rc[k] = w;
+      });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < nl; ++k) {
+      if (lane_rc[k] < 0) { if (rc >= 0) { rc = lane_rc[k]; ctx->err = lanes[k]->err; } }
+      else worst = std::max(worst, lane_rc[k]);
+      if (lane_dp[k] && rc >= 0) add_into_kernel<<<(m.nparams + 255) / 256, 256, 0, ctx->stream>>>(dp_d, lane_dp[k], m.nparams);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < nl; ++k) {
+      free_temps(lanes[k], lane_tmp[k]);
+      dfree(lanes[k], lane_dp[k]);
+    }
   }
   if (rc >= 0 && dp && o->ptr_kind == B200_PTR_HOST) from_device(ctx, dp, dp_d, (size_t)m.nparams, B200_PTR_HOST);
   cudaStreamSynchronize(ctx->stream);
