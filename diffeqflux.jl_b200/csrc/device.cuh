@@ -130,13 +130,10 @@ struct TcOp {                // one GEMM chunk for the MMA issuer
   unsigned short acc;        // accumulator column
   unsigned char new_b, last_b, layer_end, phase_end;   // phase_end: 1 = last op of the fwd/bwd phase, 2 = last wgrad op
 };
-struct TcLoad {              // one bulk load for the loader warp
-  unsigned int off, bytes;   // first piece
-  unsigned int off2, bytes2; // second piece (wgrad A: lo tile) or 0
-  unsigned char kind;        // 0: forward weight unit, 1: dgrad weight unit, 2: wgrad A buffer, 3: wgrad B buffer
-  unsigned char buf;
-  unsigned char first_w;     // first wgrad load of an RHS: scratch must be complete, fwd/bwd MMAs done
-  unsigned char first_f;     // first weight load of an RHS: previous wgrad phase done
+struct TcLoad {              // one bulk load (weight unit) for the loader warp
+  unsigned int off, bytes;
+  unsigned char kind;        // 0: forward weight unit, 1: dgrad (transposed) weight unit
+  unsigned char first_f;     // first weight load of an RHS evaluation: previous wgrad phase done, evaluation started
 };
 
 struct SolveParams {
@@ -526,10 +523,8 @@ struct StepShared {
   unsigned long long mma_done[2];        // MMAs that read A slot s have completed
   unsigned long long unit_done[TC_NB];   // MMAs that read weight slot s have completed
   unsigned long long b_full[TC_NB];      // weight unit landed in slot s
-  unsigned long long w_full[4];          // wgrad operand buffer landed (A0, A1, B0, B1)
+  unsigned long long w_full[4];          // (TC_WORKERS arrivals) wgrad operand buffer filled by the workers (A0, A1, B0, B1)
   unsigned long long w_done[4];          // MMAs that read that buffer have completed
-  unsigned long long w_ready;            // (TC_WORKERS arrivals) scratch of this RHS complete
-  unsigned long long fb_done;            // forward/backward MMAs of this RHS complete
   unsigned long long w_all_done;         // wgrad MMAs of this RHS complete
   unsigned long long wacc_done;          // a wgrad layer's accumulators are complete
   unsigned long long mu_full[2];         // mu phase: slab slices staged in the operand buffers landed
