@@ -598,7 +598,8 @@ struct Solver {
 
   // Grid barrier; thread 0 publishes this CTA's two partial sums first.  Afterwards ss.sums holds
   // the batch-wide (and cross-rank) totals, identical on every CTA and rank.
-  __device__ void barrier_reduce(double p0, double p1) {
+  // `cross`: also sum over the ranks (one NVLink round trip); a barrier that only orders this GPU's CTAs skips it
+  __device__ void barrier_reduce(double p0, double p1, bool cross = true) {
     // block reduce (deterministic order)
     p0 = warp_sum_d(p0);
     p1 = warp_sum_d(p1);
@@ -648,7 +649,7 @@ struct Solver {
       }
     }
     sync();
-    if (P.world > 1) cross_rank_exchange();
+    if (P.world > 1 && cross) cross_rank_exchange();
     if (tid == 0) {
       ss.epoch += 1u;
       ss.aborted = ld_volatile_i32(&c->abort_flag);

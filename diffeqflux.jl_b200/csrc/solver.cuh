@@ -317,7 +317,7 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
     qf[1] += clock64() - q_t0; q_t0 = clock64();
 #endif
     if constexpr (T::adj) {
-      S.barrier_reduce(0.0, 0.0);   // every CTA's SA / SE / G7 complete
+      S.barrier_reduce(0.0, 0.0, false);   // every CTA's slabs of this step complete (local ordering only)
 #ifdef B200_TC_PROF
       qf[2] += clock64() - q_t0; q_t0 = clock64();
 #endif
