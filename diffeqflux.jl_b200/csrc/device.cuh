@@ -1387,19 +1387,18 @@ struct Solver {
     float* stage = reinterpret_cast<float*>(tc_base());
     constexpr int BUF = MU_CB * NSLAB * MU_SUB;       // floats per staging buffer
     const int nb = (P.nctas + MU_CB - 1) / MU_CB;
-    auto issue = [&](int b) {                         // one thread
-      const int buf = b & 1, c0 = b * MU_CB, cn = min(MU_CB, P.nctas - c0);
+    auto issue = [&](int b) {                         // all threads: one copy each (a single issuing thread spent
+      const int buf = b & 1, c0 = b * MU_CB, cn = min(MU_CB, P.nctas - c0);   // ~1/3 of the phase issuing 21 copies per batch)
       uint64_t* bar = reinterpret_cast<uint64_t*>(&ss.mu_full[buf]);
-      mbar_arrive_expect_tx(bar, (uint32_t)(cn * NSLAB * n * 4));
-      for (int c = 0; c < cn; ++c)
-        for (int sl = 0; sl < NSLAB; ++sl)
-          bulk_g2s(stage + buf * BUF + (c * NSLAB + sl) * MU_SUB, P.slabs + ((long long)(c0 + c) * NSLAB + sl) * pp + slo,
-                   (uint32_t)(n * 4), bar);
+      if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(cn * NSLAB * n * 4));
+      if (tid < cn * NSLAB) {
+        const int c = tid / NSLAB, sl = tid - c * NSLAB;
+        bulk_g2s(stage + buf * BUF + (c * NSLAB + sl) * MU_SUB, P.slabs + ((long long)(c0 + c) * NSLAB + sl) * pp + slo,
+                 (uint32_t)(n * 4), bar);
+      }
     };
-    if (tid == 0) {
-      issue(0);
-      if (nb > 1) issue(1);
-    }
+    issue(0);
+    if (nb > 1) issue(1);
 #pragma unroll
     for (int k = 0; k < MU_SUB / NTHREADS; ++k) T0[k] = T1[k] = 0.0;
     for (int b = 0; b < nb; ++b) {
@@ -1428,7 +1427,7 @@ struct Solver {
         }
       }
       sync();                                         // buffer drained by every thread
-      if (tid == 0 && b + 2 < nb) issue(b + 2);
+      if (b + 2 < nb) issue(b + 2);
     }
   }
   // every CTA advances the mu-exchange epoch together (call after mu_reduce, CTA-uniformly)
