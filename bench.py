@@ -60,7 +60,7 @@ def peaks():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE adjoint solve-kernel launch at this workload (ncu --set full capture
 # of the final round-1 build, profiles/solve_kernels_r1_final_raw.csv); algorithmic bytes are ~0 (the path is tensor bound)
-ADJ_DRAM_BYTES_PER_LAUNCH = 30.814436e9 + 29.052224e9
+ADJ_DRAM_BYTES_PER_LAUNCH = 30.955821e9 + 29.046970e9
 
 
 class ClockSampler:
