@@ -108,3 +108,22 @@ def test_product_path_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".jl")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_header_compiles_as_c_and_links(tmp_path):
+    """The boundary is plain C: tests/c_abi_smoke.c (gcc -std=c99 -Wall -Werror) includes include/b200node.h, links
+    against libb200node.so and calls the entry points that need no device.  Without a GPU b200_ctx_create must
+    fail loudly (B200_ERR_CUDA) -- there is no CPU path."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    libdir = os.path.dirname(N.LIB_PATH)
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), os.path.join(here, "c_abi_smoke.c"),
+                    "-L" + libdir, "-lb200node", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "c abi ok, sizeof(b200_opts)=72 sizeof(b200_stats)=64" in out
