@@ -117,7 +117,14 @@ constexpr int TC_WORKERS = B200_TC_WORKERS;  // epilogue/producer threads: the 2
 constexpr int TC_CW = 32 / (TC_WORKERS / 128);   // columns of a 32-wide chunk owned by one worker thread
 constexpr int TC_NQ = TC_CW / 4;
 static_assert(TC_WORKERS == 256 || TC_WORKERS == 512, "worker threads: 8 or 16 warps");
-constexpr int TC_THREADS = TC_WORKERS + 64;  // worker warps + MMA-issuer warp + loader warp (warps 8 and 9)
+constexpr int TC_THREADS = TC_WORKERS + 128; // worker warps + one control warpgroup (warps 8..11: MMA issuer, loader, 2 spare)
+// Register reallocation (setmaxnreg): the kernel is launched at the uniform cap 65536 / TC_THREADS; the control
+// warpgroup then drops to TC_REGS_CTRL and the worker warpgroups take TC_REGS_WORK each.
+#if B200_TC_WORKERS == 256
+constexpr int TC_REGS_CTRL = 40, TC_REGS_WORK = 232;    // 128*40 + 256*232 = 64512 <= 65536
+#else
+constexpr int TC_REGS_CTRL = 32, TC_REGS_WORK = 112;    // launch cap 96: 128*32 + 512*112 = 61440 = 640*96
+#endif
 constexpr int TC_SMEM = 2 * TC_A_SLOT + TC_NB * TC_B_SLOT + 1024;
 constexpr int TC_MAX_OPS = 3 * MAXL_TC * 8;
 constexpr int TC_MAX_LOADS = 2 * MAXL_TC * 16 + MAXL_TC * 12;

@@ -5,8 +5,8 @@
 
 namespace b200 {
 
-// The tensor-core translation unit (tc_kernels.cu) launches TC_THREADS threads (320, or 576 with helper warps:
-// 18 warps put 5 on one SM sub-partition of 16 K registers, which caps the kernel at 96 registers per thread).
+// The tensor-core translation unit (tc_kernels.cu) launches TC_THREADS threads: 2 (or 4) worker warpgroups + one
+// control warpgroup; setmaxnreg moves the control group's registers to the workers right after tc_init.
 #ifdef B200_TC_TU
 #define B200_KERNEL_ATTR __launch_bounds__(TC_THREADS, 1)
 #else
@@ -47,8 +47,14 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
   __syncthreads();
   if constexpr (TC) {
     S.tc_init();
-    if (tid >= NTHREADS) {      // control warps: weight loader + MMA issuer
+    if (tid >= NTHREADS && tid < NTHREADS + 128) {      // control warpgroup: MMA issuer + weight loader
+      b200tc::reg_dec<TC_REGS_CTRL>();
       S.tc_control();
+      return;
+    }
+    b200tc::reg_inc<TC_REGS_WORK>();
+    if (tid >= NTHREADS + 128) {                        // helper worker warpgroups (TC_WORKERS = 512)
+      S.tc_helper();
       return;
     }
   }

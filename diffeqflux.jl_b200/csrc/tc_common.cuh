@@ -177,6 +177,12 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// ---- register reallocation between warpgroups (setmaxnreg; executed by every warp of a 4-warp group) -----------
+template <uint32_t R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <uint32_t R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
 // ---- 3xTF32 split -------------------------------------------------------------------------------
 // round-to-nearest (ties away from zero) to the 10-bit tf32 mantissa with two integer instructions; bit-identical
 // to cvt.rna.tf32.f32 for finite inputs (ptxas expands the cvt into FSETP + IADD + SEL + LOP3)

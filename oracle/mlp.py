@@ -60,13 +60,49 @@ def _d2act(a, pre, h):
     raise ValueError(a)
 
 
+def _tf32_rn(x):
+    """round-to-nearest (ties away) to the 10-bit tf32 mantissa: csrc/tc_common.cuh tf32_rn."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _split_tf32(x):
+    hi = _tf32_rn(x)
+    lo = _tf32_rn((np.asarray(x, np.float32) - hi).astype(np.float32))
+    return hi.astype(np.float64), lo.astype(np.float64)
+
+
+def _mm_3xtf32(a, b):
+    """Model of the tcgen05 engine's 3xTF32 GEMM: operands split into hi/lo tf32, lo*hi + hi*lo + hi*hi summed without
+    intermediate rounding (fp64 here; the tensor core's fp32 accumulator rounds far less often than an FMA chain),
+    one rounding to fp32 at the end.  The lo*lo term is dropped as on the GPU (relative error ~2^-22 per product)."""
+    ah, al = _split_tf32(a)
+    bh, bl = _split_tf32(b)
+    return (al @ bh + ah @ bl + ah @ bh).astype(np.float32)
+
+
 class MLP:
-    def __init__(self, dims, acts, pre=PRE_NONE, dtype=np.float32):
+    def __init__(self, dims, acts, pre=PRE_NONE, dtype=np.float32, wgrad_accum="blas", gemm_accum="blas"):
         self.dims = list(dims)
         self.acts = list(acts)
         assert len(self.acts) == len(self.dims) - 1
         self.pre = pre
         self.dtype = dtype
+        # How the batch contraction of the parameter gradient (K = batch) is accumulated.  The reference
+        # leaves this to its BLAS (sgemm blocking/threading is implementation-defined), so it is a named
+        # switch (SURVEY.md H1):
+        #   "blas"  one fp32 sgemm over the whole batch (what Zygote's `a' * d` does on the CPU)
+        #   "fp64"  exact: fp64 accumulation, rounded to fp32 once
+        #   ("tile", n)  fp32 sgemm per n-trajectory tile, tiles summed in fp64 in order, rounded once
+        #   ("tile_defer", n)  the accumulation order of the CUDA path: vjp returns the per-tile fp32 partials
+        #           [ntiles, P]; the integrator combines the stages per tile in fp32 and only then sums the
+        #           tiles in fp64 (oracle/tsit5.py, "deferred-sum blocks")
+        self.wgrad_accum = wgrad_accum
+        # Accumulation of the layer GEMMs (forward h W and cotangent d W^T): "blas" = fp32 sgemm (CPU reference and
+        # the FP32-FFMA engine); "fp64" = products and sums exact to fp64, rounded to fp32 once per output -- the
+        # model of the tcgen05 engine, whose 3xTF32 products carry 2^-22 relative error but whose accumulator does
+        # not round after every FMA (less rounding NOISE between neighbouring stage evaluations than an fp32 chain).
+        self.gemm_accum = gemm_accum
         self.offsets = []
         o = 0
         for i, n in zip(self.dims[:-1], self.dims[1:]):
@@ -96,11 +132,19 @@ class MLP:
         hs, pres = [h0], []
         h = h0
         for (W, b), a in zip(Wb, self.acts):
-            pre = (h @ W + b).astype(self.dtype, copy=False)
+            pre = (self._mm(h, W) + b).astype(self.dtype, copy=False)
             h = _act(a, pre).astype(self.dtype, copy=False)
             pres.append(pre)
             hs.append(h)
         return h, (x, hs, pres, Wb)
+
+    def _mm(self, a, b):
+        if self.dtype != np.float32 or self.gemm_accum == "blas":
+            return a @ b
+        if self.gemm_accum == "fp64":
+            return (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+        assert self.gemm_accum == "3xtf32"
+        return _mm_3xtf32(a, b)
 
     def __call__(self, p, x):
         return self.forward(p, x)[0]
@@ -108,19 +152,49 @@ class MLP:
     def vjp(self, cache, ybar, want_dp=True):
         """(xbar, pbar) = ybar^T d(model)/d(x, p); pbar summed over the batch."""
         x, hs, pres, Wb = cache
-        pbar = np.zeros(self.nparams, dtype=self.dtype) if want_dp else None
+        defer = isinstance(self.wgrad_accum, tuple) and self.wgrad_accum[0] == "tile_defer"
+        if defer and want_dp:
+            nt = -(-x.shape[0] // self.wgrad_accum[1])
+            pbar = np.zeros((nt, self.nparams), dtype=self.dtype)
+        else:
+            pbar = np.zeros(self.nparams, dtype=self.dtype) if want_dp else None
         hbar = np.asarray(ybar, dtype=self.dtype)
         for l in range(len(Wb) - 1, -1, -1):
             W, _ = Wb[l]
             d = (hbar * _dact(self.acts[l], pres[l], hs[l + 1])).astype(self.dtype, copy=False)
             if want_dp:
                 ow, ob = self.offsets[l]
-                pbar[ow:ob] = (hs[l].T @ d).reshape(-1)
-                pbar[ob:ob + self.dims[l + 1]] = d.sum(axis=0)
-            hbar = (d @ W.T).astype(self.dtype, copy=False)
+                gw, gb = self._wgrad(hs[l], d)
+                pbar[..., ow:ob] = gw.reshape(gw.shape[:-2] + (-1,))
+                pbar[..., ob:ob + self.dims[l + 1]] = gb
+            hbar = self._mm(d, W.T).astype(self.dtype, copy=False)
         if self.pre == PRE_CUBE:
             hbar = hbar * (3 * x * x)
         return hbar.astype(self.dtype, copy=False), pbar
+
+    def _wgrad(self, a, d):
+        """(a^T d, column sums of d) over the batch with the configured accumulation (see __init__)."""
+        mode = self.wgrad_accum
+        if mode == "blas" or self.dtype != np.float32:
+            return a.T @ d, d.sum(axis=0)
+        if mode == "fp64":
+            a64, d64 = a.astype(np.float64), d.astype(np.float64)
+            return (a64.T @ d64).astype(np.float32), d64.sum(axis=0).astype(np.float32)
+        kind, n = mode
+        if kind == "tile_defer":
+            nt = -(-a.shape[0] // n)
+            mm = _mm_3xtf32 if self.gemm_accum == "3xtf32" else (lambda x, y: x @ y)
+            gw = np.stack([mm(np.ascontiguousarray(a[i * n:(i + 1) * n].T), d[i * n:(i + 1) * n]) for i in range(nt)])
+            gb = np.stack([d[i * n:(i + 1) * n].sum(axis=0, dtype=np.float32) for i in range(nt)])
+            return gw, gb
+        assert kind == "tile"
+        gw = np.zeros((a.shape[1], d.shape[1]), np.float64)
+        gb = np.zeros(d.shape[1], np.float64)
+        for r0 in range(0, a.shape[0], n):
+            at, dt = a[r0:r0 + n], d[r0:r0 + n]
+            gw += (at.T @ dt).astype(np.float64)
+            gb += dt.sum(axis=0, dtype=np.float32).astype(np.float64)
+        return gw.astype(np.float32), gb.astype(np.float32)
 
     # ---- second order: gradient of Phi = <lz, m(z)> - ll * <e, J(z) e> wrt (z, p) -------------
     def jvp_forward(self, p, z, e):

@@ -103,11 +103,40 @@ def _axpy_stage(u, ks, coefs, dt):
     """u + dt*(sum_j coefs[j]*ks[j]) for every block of the state."""
     out = []
     for b in range(len(u)):
+        if _is_deferred(u[b], ks[0][b]):
+            out.append(u[b])            # never read by the RHS; updated at the end of the step
+            continue
         acc = coefs[0] * ks[0][b]
         for j in range(1, len(coefs)):
             acc = acc + coefs[j] * ks[j][b]
         out.append((u[b] + dt * acc).astype(np.float32, copy=False))
     return out
+
+
+def _fma32(a, b, c):
+    """float32 fused multiply-add (the product of two float32 is exact in float64)."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def _is_deferred(u_block, k_block) -> bool:
+    """A "deferred-sum" block: its derivative arrives as per-tile partial sums [ntiles, ...] (the parameter
+    gradient of the adjoint with MLP(wgrad_accum=("tile_defer", n))).  The RHS never reads such a block, so
+    stage values are not formed; at the end of a step the stage combinations are taken per tile in float32
+    (FMA chain in stage order) and the tiles are summed in float64 -- the accumulation order of the CUDA path
+    (csrc/device.cuh: step_local / mu_reduce)."""
+    return k_block.ndim == u_block.ndim + 1
+
+
+def _deferred_total(k_block):
+    return np.sum(k_block, axis=0, dtype=np.float64).astype(np.float32)
+
+
+def _deferred_combo(ks, b, coefs):
+    """sum over tiles (float64) of the per-tile float32 FMA chain  coefs[0]*k1 + coefs[1]*k2 + ..."""
+    acc = (coefs[0] * ks[0][b]).astype(np.float32)
+    for j in range(1, len(coefs)):
+        acc = _fma32(coefs[j], ks[j][b], acc)
+    return np.sum(acc, axis=0, dtype=np.float64).astype(np.float32)
 
 
 def _sumsq(blocks) -> float:
@@ -205,6 +234,7 @@ def initial_dt(rhs, u0, t0, tdir, dtmax, abstol, reltol, stats: Stats) -> np.flo
     d0 = rms_norm([x / s for x, s in zip(u0, sk)])
     f0 = rhs(u0, t0)
     stats.nf += 1
+    f0 = [_deferred_total(f) if _is_deferred(x, f) else f for x, f in zip(u0, f0)]
     d1 = rms_norm([x / s for x, s in zip(f0, sk)])
     smalldt = f32(1e-6)
     if d0 < f32(1e-5) or d1 < f32(1e-5):
@@ -218,6 +248,7 @@ def initial_dt(rhs, u0, t0, tdir, dtmax, abstol, reltol, stats: Stats) -> np.flo
     u1 = [(x + dt0_t * f).astype(np.float32) for x, f in zip(u0, f0)]
     f1 = rhs(u1, f32(t0 + dt0_t))
     stats.nf += 1
+    f1 = [_deferred_total(f) if _is_deferred(x, f) else f for x, f in zip(u0, f1)]
     d2 = f32(rms_norm([(a - b) / s for a, b, s in zip(f1, f0, sk)]) / dt0)
     mx = max(d1, d2)
     if mx <= f32(1e-15):
@@ -294,6 +325,15 @@ def solve(rhs, u0, t0, t1, *, abstol=1e-6, reltol=1e-3, saveat=(), save_start=Tr
         # embedded error estimate
         num = 0.0
         for b in range(len(u)):
+            if _is_deferred(u[b], ks[0][b]):
+                tot_a = _deferred_combo(ks, b, [A[(7, j)] for j in range(1, 7)])
+                tot_e = _deferred_combo(ks, b, BTILDE)
+                unew[b] = _fma32(dt, tot_a, u[b])
+                ut = (dt * tot_e).astype(np.float32)
+                sk = _fma32(np.maximum(np.abs(u[b]), np.abs(unew[b])), reltol, abstol)
+                r = (ut / sk).astype(np.float32)
+                num += float(np.sum(np.square(r, dtype=np.float32), dtype=np.float64))
+                continue
             acc = BTILDE[0] * ks[0][b]
             for j in range(1, 7):
                 acc = acc + BTILDE[j] * ks[j][b]

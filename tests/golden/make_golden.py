@@ -13,6 +13,10 @@ Cases mirror the reference's own tests for the path:
   batched     neural_de_tests.jl batched input with BacksolveAdjoint, widths the tcgen05 engine takes
   ffjord      test/CNF/cnf_tests.jl monte-carlo branch (2 -> 16 -> 2 tanh), fixed noise seed
   mshoot      test/MultipleShooting group_ranges + grouped solves
+  headline    BASELINE.json configs[1] at FULL size on bench.py's exact inputs (B = 16384, 64 -> 256 -> 256 -> 64,
+              Tsit5 1e-6, BacksolveAdjoint): step statistics, per-step (t, dt, EEst) traces, dp and strided slices
+              of u(t1) / du0, for the three accumulation models of the oracle (see oracle/mlp.py) -- ~3 minutes;
+              only regenerated with `make_golden.py headline`
 
 Run from the repo root:  python tests/golden/make_golden.py
 """
@@ -96,7 +100,32 @@ def mshoot():
              ranges_21_5=np.array(omshoot.group_ranges(21, 5), np.int64))
 
 
+def headline():
+    import zlib
+    import bench
+    p, u0 = bench.synth(bench.BATCH)
+    out = dict(p_crc=np.int64(zlib.crc32(p.tobytes())), u0_crc=np.int64(zlib.crc32(u0.tobytes())), batch=np.int64(bench.BATCH))
+    kw = dict(abstol=bench.TOL, reltol=bench.TOL)
+    # model name -> (wgrad accumulation, layer-GEMM accumulation); "defer" is the parity target of the CUDA path
+    models = {"blas": ("blas", "blas"), "defer": (("tile_defer", 128), "blas"), "exactgemm": (("tile", 128), "fp64")}
+    for name, (wacc, gacc) in models.items():
+        mlp = MLP(bench.DIMS, [ACT_TANH, ACT_TANH, ACT_ID], wgrad_accum=wacc, gemm_accum=gacc)
+        prob = onode.NodeProblem(mlp)
+        fw = onode.forward(prob, p, u0, bench.TSPAN[0], bench.TSPAN[1], save_everystep=False, save_start=False, record_trace=True, **kw)
+        adj = onode.adjoint(prob, p, fw, np.ones_like(fw.us), sensealg=onode.SENSE_BACKSOLVE, record_trace=True, **kw)
+        print("headline", name, stats_vec(fw.stats), stats_vec(adj.stats), flush=True)
+        out[f"{name}_fwd_stats"], out[f"{name}_adj_stats"] = stats_vec(fw.stats), stats_vec(adj.stats)
+        out[f"{name}_fwd_trace"] = np.array(fw.stats.trace, np.float32)
+        out[f"{name}_adj_trace"] = np.array(adj.stats.trace, np.float32)
+        if name == "defer":
+            out.update(dp=adj.dp, du0_s=adj.du0[::64].copy(), uT_s=fw.us[-1][::64].copy())
+    np.savez_compressed(os.path.join(HERE, "headline.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "headline":
+        headline()
+        sys.exit(0)
     spiral()
     batched()
     ffjord()
