@@ -44,6 +44,7 @@ struct b200_ctx {
   // sub-contexts (own stream, control block, workspace cache), one host thread per sub-context
   std::vector<b200_ctx*> subs;
   bool owns_stream = false;
+  std::vector<b200_tape*> tapes;  // live tapes that own blocks of this context (neutralised by b200_ctx_destroy)
   // diagnostics
   float* trace_dev = nullptr;
   int trace_cap = 0;
@@ -82,6 +83,20 @@ struct b200_tape {
   unsigned long long seed = 0;
   int noise_per_call = 1;
   int b_offset = 0;
+};
+
+// Every entry point binds the context's device for the duration of the call and restores the caller's device
+// afterwards (a host framework may be working on another GPU).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
 };
 
 static int set_err(b200_ctx* ctx, int code, const char* fmt, ...) {
@@ -166,7 +181,9 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
     delete ctx;
     return B200_ERR_CUDA;
   }
-  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return B200_ERR_CUDA; }
+  DeviceGuard guard(device);
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != device) { delete ctx; return B200_ERR_CUDA; }
   cudaDeviceProp prop{};
   cudaGetDeviceProperties(&prop, device);
   ctx->num_sms = prop.multiProcessorCount;
@@ -176,11 +193,6 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
   cudaEventCreate(&ctx->ev1);
   cudaMalloc(&ctx->ctrl_dev, sizeof(Ctrl));
   cudaMallocHost(&ctx->ctrl_host, sizeof(Ctrl));
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    unsigned long long thr = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   const Tableau tab = host_tableau();
   if (cudaMemcpyToSymbol(c_tab, &tab, sizeof tab) != cudaSuccess || b200_tc_init_tableau() != cudaSuccess) { delete ctx; return B200_ERR_CUDA; }
   *out = ctx;
@@ -189,10 +201,13 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
 
 extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx->device);
   for (b200_ctx* sub : ctx->subs) b200_ctx_destroy(sub);
   ctx->subs.clear();
   cudaStreamSynchronize(ctx->stream);
+  // tapes that outlive their context keep no device memory: b200_tape_free on them only releases the host object
+  for (b200_tape* t : ctx->tapes) t->ctx = nullptr;
+  ctx->tapes.clear();
   for (int r = 0; r < ctx->world; ++r)
     if (ctx->peers[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peers[r]);
   for (auto& b : ctx->blocks) cudaFree(b.ptr);
@@ -208,7 +223,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
 
 extern "C" int b200_ctx_trace(b200_ctx* ctx, int capacity, float* out, int max_entries) {
   if (!ctx) return B200_ERR_ARG;
-  CU(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
   if (capacity >= 0 && capacity != ctx->trace_cap) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->trace_dev) CU(cudaFree(ctx->trace_dev));
@@ -232,6 +247,7 @@ extern "C" const char* b200_last_error(b200_ctx* ctx) { return ctx ? ctx->err.c_
 
 extern "C" int b200_ctx_sync(b200_ctx* ctx) {
   if (!ctx) return B200_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -447,6 +463,23 @@ static cudaError_t launch_any(int flavor, const SolveParams& P, int smem_bytes, 
     default: return launch_flavor<FL_ADJ_FFJORD>(P, smem_bytes, s);
   }
 }
+template <int FL>
+static cudaError_t static_smem_flavor(int* bytes) {
+  cudaFuncAttributes a{};
+  cudaError_t e = cudaFuncGetAttributes(&a, solve_kernel<FL>);
+  *bytes = (int)a.sharedSizeBytes;
+  return e;
+}
+// bytes of static __shared__ (StepShared) a flavour's kernel carries beside its dynamic shared memory
+static cudaError_t static_smem_any(int flavor, int* bytes) {
+  switch (flavor) {
+    case FL_FWD_NODE: return static_smem_flavor<FL_FWD_NODE>(bytes);
+    case FL_FWD_FFJORD: return static_smem_flavor<FL_FWD_FFJORD>(bytes);
+    case FL_ADJ_NODE_INTERP: return static_smem_flavor<FL_ADJ_NODE_INTERP>(bytes);
+    case FL_ADJ_NODE_BACKSOLVE: return static_smem_flavor<FL_ADJ_NODE_BACKSOLVE>(bytes);
+    default: return static_smem_flavor<FL_ADJ_FFJORD>(bytes);
+  }
+}
 static cudaError_t occupancy_any(int flavor, int smem_bytes, int* n) {
   switch (flavor) {
     case FL_FWD_NODE: return occupancy_flavor<FL_FWD_NODE>(smem_bytes, n);
@@ -457,10 +490,14 @@ static cudaError_t occupancy_any(int flavor, int smem_bytes, int* n) {
   }
 }
 
+static int cudaFuncAttributes_ok(cudaError_t e) { return e == cudaSuccess ? 0 : 1; }
 // choose the tile (trajectories per CTA pass) and the grid
 static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int tile_opt, SolveParams& P,
                       int* smem_bytes) {
-  const int budget = ctx->smem_optin - 2048;   // static __shared__ StepShared lives beside it
+  int static_bytes = 0;                        // static __shared__ StepShared lives beside the dynamic part
+  if (cudaFuncAttributes_ok(static_smem_any(flavor, &static_bytes)) != 0)
+    return set_err(ctx, B200_ERR_CUDA, "cudaFuncGetAttributes failed");
+  const int budget = ctx->smem_optin - static_bytes;
   int best = 0;
   double best_cost = 1e300;
   SmemPlan sp;
@@ -569,7 +606,9 @@ static void free_temps(b200_ctx* ctx, std::vector<void*>& temps) {
 extern "C" void b200_tape_free(b200_tape* t) {
   if (!t) return;
   b200_ctx* ctx = t->ctx;
-  cudaSetDevice(ctx->device);
+  if (!ctx) { delete t; return; }            // its context is gone (and took the device memory with it)
+  DeviceGuard guard(ctx->device);
+  ctx->tapes.erase(std::remove(ctx->tapes.begin(), ctx->tapes.end(), t), ctx->tapes.end());
   dfree(ctx, t->wp); dfree(ctx, t->wtp); dfree(ctx, t->wimg); dfree(ctx, t->ring); dfree(ctx, t->k1_first);
   dfree(ctx, t->step_t); dfree(ctx, t->out_u); dfree(ctx, t->out_t); dfree(ctx, t->final_state);
   delete t;
@@ -579,7 +618,8 @@ extern "C" int b200_tape_nsteps(const b200_tape* t) { return t ? t->nsteps : B20
 extern "C" int b200_tape_steps(b200_ctx* ctx, const b200_tape* t, float* ts, float* us, int ptr_kind) {
   if (!ctx || !t) return B200_ERR_ARG;
   if (!t->dense) return set_err(ctx, B200_ERR_ARG, "tape holds no dense record (sensealg != Interpolating)");
-  CU(cudaSetDevice(ctx->device));
+  if (t->ctx != ctx) return set_err(ctx, B200_ERR_ARG, "tape belongs to another (or a destroyed) context");
+  DeviceGuard guard(ctx->device);
   const int n = t->nsteps;
   if (ts) { int rc = from_device(ctx, ts, t->step_t, n + 1, ptr_kind); if (rc) return rc; }
   if (us) {
@@ -603,6 +643,7 @@ static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, cons
   const int D = m.dims[0];
   const int NS = (flavor == FL_FWD_FFJORD) ? D + 1 : D;
   b200_tape* t = new b200_tape();
+  ctx->tapes.push_back(t);
   t->ctx = ctx; t->m = m; t->fwd_flavor = flavor; t->sensealg = o->sensealg;
   t->B = B; t->NS = NS; t->D = D; t->d_in = d_in; t->augment = augment; t->t0 = t0; t->t1 = t1;
   t->seed = o->seed; t->noise_per_call = o->noise_per_call; t->b_offset = o->b_offset;
@@ -726,8 +767,6 @@ static int check_common(b200_ctx* ctx, const b200_model* model, const b200_opts*
   if (model->m.dims[0] != model->m.dims[model->m.nl])
     return set_err(ctx, B200_ERR_ARG, "model maps %d -> %d: an ODE right-hand side must preserve the state size",
                    model->m.dims[0], model->m.dims[model->m.nl]);
-  cudaError_t e = cudaSetDevice(ctx->device);
-  if (e != cudaSuccess) return set_err(ctx, B200_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -737,8 +776,11 @@ extern "C" int b200_node_forward(b200_ctx* ctx, const b200_model* model, const f
                                  b200_stats* stats, b200_tape** tape) {
   int rc = check_common(ctx, model, o, B);
   if (rc) return rc;
+  DeviceGuard guard(ctx->device);
   const MlpDesc& m = model->m;
   if (!p || !u0) return set_err(ctx, B200_ERR_ARG, "null p/u0");
+  if (o->save_everystep && !tape)
+    return set_err(ctx, B200_ERR_ARG, "save_everystep needs a tape: the accepted steps are fetched with b200_tape_steps");
   if (d_in < 1 || augment < 0 || d_in + augment != m.dims[0])
     return set_err(ctx, B200_ERR_ARG, "state size mismatch: d_in %d + augment %d != model input %d", d_in, augment, m.dims[0]);
   if (nsave < 0 || (nsave > 0 && !saveat)) return set_err(ctx, B200_ERR_ARG, "saveat");
@@ -852,7 +894,9 @@ extern "C" int b200_node_adjoint(b200_ctx* ctx, const b200_model* model, b200_ta
                                  const b200_opts* o, float* du0, float* dp, b200_stats* stats) {
   int rc = check_common(ctx, model, o, tape ? tape->B : 0);
   if (rc) return rc;
+  DeviceGuard guard(ctx->device);
   if (!tape || !dL_du) return set_err(ctx, B200_ERR_ARG, "null tape/dL_du");
+  if (tape->ctx != ctx) return set_err(ctx, B200_ERR_ARG, "tape belongs to another (or a destroyed) context");
   if (tape->fwd_flavor != FL_FWD_NODE) return set_err(ctx, B200_ERR_ARG, "tape was not recorded by b200_node_forward");
   if (tape->sensealg != B200_SENSE_INTERPOLATING && tape->sensealg != B200_SENSE_BACKSOLVE)
     return set_err(ctx, B200_ERR_ARG, "tape recorded with sensealg %d", tape->sensealg);
@@ -897,6 +941,7 @@ extern "C" int b200_ffjord_forward(b200_ctx* ctx, const b200_model* model, const
                                    float* z_out, b200_stats* stats, b200_tape** tape) {
   int rc = check_common(ctx, model, o_in, B);
   if (rc) return rc;
+  DeviceGuard guard(ctx->device);
   const MlpDesc& m = model->m;
   if (!p || !x) return set_err(ctx, B200_ERR_ARG, "null p/x");
   if (m.pre != B200_PRE_NONE) return set_err(ctx, B200_ERR_UNSUPPORTED, "FFJORD does not support a pre-layer");
@@ -936,7 +981,9 @@ extern "C" int b200_ffjord_adjoint(b200_ctx* ctx, const b200_model* model, b200_
                                    b200_stats* stats) {
   int rc = check_common(ctx, model, o, tape ? tape->B : 0);
   if (rc) return rc;
+  DeviceGuard guard(ctx->device);
   if (!tape || !dL_dlogpx) return set_err(ctx, B200_ERR_ARG, "null tape/dL_dlogpx");
+  if (tape->ctx != ctx) return set_err(ctx, B200_ERR_ARG, "tape belongs to another (or a destroyed) context");
   if (tape->fwd_flavor != FL_FWD_FFJORD || !tape->dense)
     return set_err(ctx, B200_ERR_ARG, "tape was not recorded by b200_ffjord_forward with InterpolatingAdjoint");
   const int B = tape->B, D = tape->D;
@@ -1020,7 +1067,9 @@ extern "C" int b200_mshoot_forward(b200_ctx* ctx, const b200_model* model, const
                                    b200_stats* stats, b200_tape** tapes) {
   int rc = check_common(ctx, model, o_in, B);
   if (rc) return rc;
+  DeviceGuard guard(ctx->device);
   if (!p || !ode_data || !tsteps || !first || !last || G < 1 || T < 2) return set_err(ctx, B200_ERR_ARG, "mshoot arguments");
+  if (tapes) for (int g = 0; g < G; ++g) tapes[g] = nullptr;
   const MlpDesc& m = model->m;
   const int D = m.dims[0];
   b200_opts o = *o_in;
@@ -1097,6 +1146,9 @@ extern "C" int b200_mshoot_forward(b200_ctx* ctx, const b200_model* model, const
   }
   cudaStreamSynchronize(ctx->stream);
   free_temps(ctx, temps);
+  if (rc < 0 && tapes)                       // a group failed: release the tapes the other groups already produced
+    for (int g = 0; g < G; ++g)
+      if (tapes[g]) { b200_tape_free(tapes[g]); tapes[g] = nullptr; }
   return rc < 0 ? rc : worst;
 }
 
@@ -1106,6 +1158,13 @@ extern "C" int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_
   if (!ctx || !tapes || G < 1 || !tapes[0]) return B200_ERR_ARG;
   int rc = check_common(ctx, model, o, tapes[0]->B);
   if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  for (int g = 0; g < G; ++g) {
+    if (!tapes[g]) return set_err(ctx, B200_ERR_ARG, "tapes[%d] is null", g);
+    b200_ctx* owner = tapes[g]->ctx;
+    if (owner != ctx && std::find(ctx->subs.begin(), ctx->subs.end(), owner) == ctx->subs.end())
+      return set_err(ctx, B200_ERR_ARG, "tapes[%d] belongs to another (or a destroyed) context", g);
+  }
   const MlpDesc& m = model->m;
   const int B = tapes[0]->B, D = tapes[0]->D;
   std::vector<void*> temps;
@@ -1198,7 +1257,7 @@ extern "C" int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_
 // ------------------------------------------------------------------------------------------------ multi-GPU plumbing
 extern "C" int b200_ctx_ipc_export(b200_ctx* ctx, unsigned char handle[B200_IPC_HANDLE_BYTES]) {
   if (!ctx || !handle) return B200_ERR_ARG;
-  CU(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
   if (!ctx->mailbox) {
     CU(cudaMalloc(&ctx->mailbox, sizeof(Mailbox)));
     CU(cudaMemset(ctx->mailbox, 0, sizeof(Mailbox)));
@@ -1215,7 +1274,7 @@ extern "C" int b200_ctx_ipc_import(b200_ctx* ctx, int rank, int world, const uns
   if (!ctx || !handles) return B200_ERR_ARG;
   if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) return set_err(ctx, B200_ERR_ARG, "rank %d / world %d", rank, world);
   if (!ctx->mailbox) return set_err(ctx, B200_ERR_ARG, "call b200_ctx_ipc_export first");
-  CU(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
   for (int r = 0; r < world; ++r) {
     if (r == rank) { ctx->peers[r] = ctx->mailbox; continue; }
     cudaIpcMemHandle_t h;
@@ -1224,6 +1283,10 @@ extern "C" int b200_ctx_ipc_import(b200_ctx* ctx, int rank, int world, const uns
     CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->peers[r] = reinterpret_cast<Mailbox*>(ptr);
   }
+  // Exchange epochs are (solve sequence number << 24 | exchange index) and must agree on all ranks: solves a rank ran on
+  // its own before joining (world == 1: no mailbox traffic) do not count.  From here on every rank must issue the same
+  // sequence of solves on this context.
+  if (ctx->world == 1) ctx->solve_seq = 0;
   ctx->rank = rank;
   ctx->world = world;
   return 0;

@@ -292,8 +292,8 @@ def _split_saveat(saveat, t0, t1, save_start, save_end, save_everystep):
         sv = np.zeros(0, np.float32)
     elif np.isscalar(saveat):
         h = f32(abs(saveat))
-        n = int(np.floor(float((t1 - t0) / h) + 1e-6))
-        sv = (t0 + h * np.arange(0, n + 1, dtype=np.float32)).astype(np.float32)
+        n = int(np.floor(float(abs(t1 - t0) / h) + 1e-6))
+        sv = (t0 + (h if t1 >= t0 else -h) * np.arange(0, n + 1, dtype=np.float32)).astype(np.float32)   # t0:h:t1 in either direction
         scalar = True
     else:
         sv = np.asarray(saveat.detach().cpu().numpy() if _is_torch(saveat) else saveat, dtype=np.float32).reshape(-1)
@@ -391,6 +391,10 @@ class _Solve:
             if not want_tape:
                 N.lib().b200_tape_free(tape)
                 tape = C.c_void_p()
+        elif st.n_out < n_out:
+            # an early exit (MaxIters / DtLessThanMin / Unstable, or t0 == t1) wrote fewer points than requested:
+            # only the rows the kernel wrote are returned, as `sol.u` of an aborted solve upstream
+            out_u, out_t = out_u[:st.n_out], out_t[:st.n_out]
         stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile, st.engine)
         return dict(ctx=ctx, mh=mh, tape=tape, out_u=out_u, out_t=out_t, rc=rc, stats=stats, vec=vec,
                     B=B, D=D, d_in=d_in, on_dev=on_dev, dev=dev, opts=o)
@@ -687,10 +691,20 @@ if torch is not None:
             run = ctx.run
             if not run.on_dev:
                 g = g.cpu().numpy()
-            dp = run.adjoint(ctx.tapes, g)
+            want_data = ctx.needs_input_grad[1]
+            dp, dblocks = run.adjoint(ctx.tapes, g, want_data)
             if not _is_torch(dp):
                 dp = torch.from_numpy(dp)
-            return dp, None, None
+            ddata = None
+            if want_data:
+                # group g starts from ode_data[first[g]] (src/multiple_shooting.jl:52-63): its initial-condition
+                # cotangent lands on that time index (neighbouring groups share a point, hence the accumulation)
+                if not _is_torch(dblocks):
+                    dblocks = torch.from_numpy(dblocks)
+                ddata = torch.zeros((len(run.tsteps),) + tuple(dblocks.shape[1:]), dtype=dblocks.dtype, device=dblocks.device)
+                for i, (a, _) in enumerate(run.ranges):
+                    ddata[a] += dblocks[i]
+            return dp, ddata, None
 
 
 class _MshootRun:
@@ -727,16 +741,18 @@ class _MshootRun:
                                                    _ptr(preds), stats, tapes))
         return preds, [C.c_void_p(t) for t in tapes], [s.as_dict() for s in stats], rc
 
-    def adjoint(self, tapes, g):
+    def adjoint(self, tapes, g, want_data=False):
+        """dp (summed over the groups) and, on request, the per-group initial-condition cotangents [G][B][D]."""
         gb = _Buf(g)
         G = len(tapes)
         arr = (C.c_void_p * G)(*[t.value for t in tapes])
         dp = _alloc((self.chain.nparams,), None, self.on_dev, self.dev)
+        dblocks = _alloc((G, self.B, self.D), None, self.on_dev, self.dev) if want_data else None
         stats = (N.Stats * G)()
         self.ctx.check(N.lib().b200_mshoot_adjoint(self.ctx._h, self.mh, arr, G, gb.ptr, C.byref(self.opts), _ptr(dp),
-                                                   None, stats))
+                                                   _ptr(dblocks), stats))
         self.adjoint_stats = [s.as_dict() for s in stats]
-        return dp
+        return dp, dblocks
 
 
 def multiple_shoot(p, ode_data, tsteps, prob: ODEProblem, loss_function, *rest, continuity_term=100, **kwargs):

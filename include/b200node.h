@@ -78,8 +78,9 @@ typedef struct b200_opts {
   uint64_t seed;         /* FFJORD Hutchinson noise seed */
   int noise_per_call;    /* 1 (default) = fresh noise for every RHS call as src/ffjord.jl:92 */
   int b_offset;          /* global index of this shard's first trajectory (noise stream, multi-GPU) */
-  int save_everystep;    /* 1: the saved points are the accepted steps (`sol.t`); needs the dense tape;
-                            fetch them with b200_tape_steps (out_u/out_t of the call stay untouched) */
+  int save_everystep;    /* 1: the saved points are the accepted steps (`sol.t`); needs the dense tape: `tape` must be
+                            non-NULL (B200_ERR_ARG otherwise) and the points are fetched with b200_tape_steps
+                            (out_u/out_t of the call stay untouched) */
   int path;              /* RHS engine: 0 = automatic, 1 = FP32-FFMA kernels only, 2 = require the tcgen05
                             3xTF32 tensor-core engine (error if the model shape is not eligible) */
   int reserved[2];
@@ -104,7 +105,9 @@ typedef struct b200_stats {
 /* ---- context / model ------------------------------------------------------------------------- */
 int b200_abi_version(void);
 /* device: CUDA ordinal; stream: a cudaStream_t to run on, or NULL for the legacy default stream
- * (the stream PyTorch / CUDA.jl use by default, so no extra synchronisation is needed). */
+ * (the stream PyTorch / CUDA.jl use by default, so no extra synchronisation is needed; a caller that works on a
+ * non-blocking stream must pass that stream here, otherwise its pending writes to u0 / p are not ordered before the
+ * solve).  Every entry point binds `device` for the duration of the call and restores the caller's device. */
 int b200_ctx_create(int device, void* stream, b200_ctx** out);
 void b200_ctx_destroy(b200_ctx* ctx);
 const char* b200_last_error(b200_ctx* ctx);
@@ -175,7 +178,8 @@ int b200_mshoot_forward(b200_ctx* ctx, const b200_model* model, const float* p,
                         const int* first, const int* last, const b200_opts* opts, float* preds,
                         b200_stats* stats, b200_tape** tapes);
 /* Sum of the per-group pullbacks: dL_dpreds laid out like preds; dp [P] (summed over groups);
- * d_data (nullable) [T][B][D] gradient w.r.t. the group initial conditions. */
+ * d_data (nullable) [G][B][D]: block g is the cotangent of group g's initial condition ode_data[first[g]];
+ * neighbouring groups share a data point, so the caller ACCUMULATES block g into time index first[g]. */
 int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_tape** tapes, int G,
                         const float* dL_dpreds, const b200_opts* opts, float* dp, float* d_data,
                         b200_stats* stats);

@@ -22,11 +22,11 @@ def load(name):
 
 
 def close(a, b, rtol, what=""):
+    """element-wise |a - b| <= rtol * |b| + rtol * max|b|"""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
     scale = max(np.abs(b).max(), 1e-30)
-    err = np.abs(a - b).max() / scale
-    assert err <= rtol, f"{what}: max err {err:.3e} of scale {scale:.3e}"
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * scale, err_msg=what)
 
 
 # ------------------------------------------------------------------------------------------ CPU: oracle vs golden
@@ -64,6 +64,48 @@ def test_oracle_reproduces_mshoot_and_ranges():
     close(dp, g["dp"], 1e-5, "dp")
 
 
+def test_headline_golden_is_consistent_with_bench_inputs():
+    """tests/golden/headline.npz (full-size oracle runs, `make_golden.py headline`) belongs to bench.py's current
+    inputs and records the three accumulation models in the documented order blas >= defer >= exactgemm."""
+    import zlib
+    import bench
+    g = load("headline")
+    p, u0 = bench.synth(int(g["batch"]))
+    assert zlib.crc32(p.tobytes()) == int(g["p_crc"]) and zlib.crc32(u0.tobytes()) == int(g["u0_crc"])
+    assert int(g["batch"]) == bench.BATCH == 16384
+    for m in ("blas", "defer", "exactgemm"):
+        f, a = g[m + "_fwd_stats"], g[m + "_adj_stats"]
+        assert f[1] == 0 and a[1] == 0 and f[3] == 0 and a[3] == 0
+        assert f[2] == 3 + 6 * f[0] and a[2] == 3 + 6 * a[0]
+        assert len(g[m + "_adj_trace"]) == a[0]
+    assert g["blas_adj_stats"][0] >= g["defer_adj_stats"][0] >= g["exactgemm_adj_stats"][0]
+    assert list(g["defer_fwd_stats"][:3]) == [19, 0, 117] and list(g["defer_adj_stats"][:3]) == [36, 0, 219]
+    assert g["dp"].shape == (p.size,)
+
+
+def test_oracle_accumulation_models_agree_at_small_batch():
+    """The oracle's accumulation switches (oracle/mlp.py: wgrad_accum / gemm_accum) change only rounding: at B = 256
+    the gradients of all models agree to 2e-6 and the per-tile deferred sums reproduce the plain totals."""
+    rng = np.random.default_rng(5)
+    dims = [32, 64, 32]
+    base = MLP(dims, [ACT_TANH, ACT_ID])
+    p = base.init(rng, scale=2.0)
+    u0 = rng.standard_normal((256, 32)).astype(np.float32)
+    kw = dict(abstol=1e-6, reltol=1e-6)
+    outs = {}
+    for name, mk in (("blas", {}), ("fp64", dict(wgrad_accum="fp64")), ("tile", dict(wgrad_accum=("tile", 128))),
+                     ("defer", dict(wgrad_accum=("tile_defer", 128))), ("3xtf32", dict(wgrad_accum=("tile_defer", 128), gemm_accum="3xtf32"))):
+        prob = onode.NodeProblem(MLP(dims, [ACT_TANH, ACT_ID], **mk))
+        fw = onode.forward(prob, p, u0, 0.0, 1.0, save_everystep=False, save_start=False, **kw)
+        adj = onode.adjoint(prob, p, fw, np.ones_like(fw.us), sensealg=1, **kw)
+        assert adj.dp.shape == p.shape and adj.stats.retcode == 0
+        outs[name] = adj
+    for name, adj in outs.items():
+        close(adj.dp, outs["fp64"].dp, 2e-6 if name != "3xtf32" else 1e-5, f"dp {name}")
+        close(adj.du0, outs["fp64"].du0, 2e-5, f"du0 {name}")
+        assert abs(adj.stats.naccept - outs["fp64"].stats.naccept) <= 2
+
+
 # ------------------------------------------------------------------------------------------ GPU: CUDA path vs golden
 @pytest.mark.gpu
 def test_gpu_spiral_matches_golden():
@@ -96,7 +138,11 @@ def test_gpu_batched_backsolve_matches_golden(path):
     du0, dp = back(np.ones_like(g["us"]))
     close(dp, g["dp"], 1e-4, "dp")
     close(du0, g["du0"], 1e-4, "du0")
-    assert abs(sol.stats.naccept - int(g["fwd_stats"][0])) <= 1 and sol.stats.nreject == int(g["fwd_stats"][1])
+    # exact accepted / rejected / nf on BOTH engines, forward and adjoint (this configuration's controller is not in
+    # the rounding-noise regime for long enough to move a step: see DESIGN.md section 2)
+    ast = node.last["adjoint_stats"]
+    assert [sol.stats.naccept, sol.stats.nreject, sol.stats.nf] == [int(x) for x in g["fwd_stats"][:3]]
+    assert [ast.naccept, ast.nreject, ast.nf] == [int(x) for x in g["adj_stats"][:3]]
 
 
 @pytest.mark.gpu

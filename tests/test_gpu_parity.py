@@ -21,11 +21,12 @@ RTOL = 1e-4
 
 
 def close(a, b, rtol=RTOL, what=""):
+    """Element-wise |a - b| <= rtol * |b| + rtol * max|b| (numpy assert_allclose with atol = rtol * scale: entries
+    much smaller than the array's scale carry the absolute rounding error of the sums they come from)."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
     scale = max(np.abs(b).max(), 1e-30)
-    err = np.abs(a - b).max() / scale
-    assert err <= rtol, f"{what}: max err {err:.3e} of scale {scale:.3e}"
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * scale, err_msg=what)
 
 
 def make(dims, seed, scale=1.0, pre=False):
@@ -47,13 +48,21 @@ def counts(st):
     return (st.naccept, st.nreject, st.nf)
 
 
-def check_steps(gpu, orc, what, exact):
+def check_steps(gpu, orc, what, exact, spread=None):
+    """exact: identical (accepted, rejected, nf).  Otherwise the configuration is in the rounding-noise / tstop-remainder
+    regime where the count follows the arithmetic's noise floor: within 15 % of the oracle's, or --
+    where `spread` holds the oracle's own counts under few-ulp perturbations of the weights -- within that spread
+    (widened by 25 %: a handful of perturbations does not exhaust it)."""
     g, o = counts(gpu), counts(orc)
     if exact:
         assert g == o, f"{what}: gpu {g} oracle {o}"
-    else:   # rounding-noise / tstop-remainder regime: same order of magnitude only
-        n_g, n_o = g[0] + g[1], o[0] + o[1]
-        assert abs(n_g - n_o) <= max(3, n_o + n_o // 4), f"{what}: gpu {g} oracle {o} (noise-dominated controller)"
+        return
+    n_g, n_o = g[0] + g[1], o[0] + o[1]
+    if spread:
+        lo, hi = min(spread + [n_o]), max(spread + [n_o])
+        assert 0.75 * lo - 2 <= n_g <= 1.25 * hi + 2, f"{what}: gpu {g} oracle {o}, oracle spread under 4-ulp perturbations {sorted(spread)}"
+    else:
+        assert abs(n_g - n_o) <= max(2, -(-15 * n_o // 100)), f"{what}: gpu {g} oracle {o} (noise-dominated controller)"
 
 
 def node_case(chain, mlp, p, u0, tspan, kw, dL_fn=None, augment=0, noisy=False, rtol=None, adj_exact=True):
@@ -80,7 +89,15 @@ def node_case(chain, mlp, p, u0, tspan, kw, dL_fn=None, augment=0, noisy=False, 
     dL = np.ones_like(fw.us) if dL_fn is None else dL_fn(fw.us)
     adj = onode.adjoint(prob, p, fw, dL, sensealg=sense, augment=augment, **tol)
     assert sol.retcode == 0 and fw.stats.retcode == 0
-    check_steps(sol.stats, fw.stats, "forward", not noisy)
+    spread_f, spread_a = [], []
+    if noisy:          # how far the oracle's own step counts move under 4-ulp perturbations of the weights
+        for seed in (1, 2, 3, 4):
+            q = perturbed(p, seed)
+            f2 = onode.forward(prob, q, u0, tspan[0], tspan[1], dense=(sense == 0), augment=augment, **okw)
+            a2 = onode.adjoint(prob, q, f2, np.ones_like(f2.us) if dL_fn is None else dL_fn(f2.us), sensealg=sense, augment=augment, **tol)
+            spread_f.append(f2.stats.naccept + f2.stats.nreject)
+            spread_a.append(a2.stats.naccept + a2.stats.nreject)
+    check_steps(sol.stats, fw.stats, "forward", not noisy, spread_f)
     arr = sol.array()[:, None, :] if vec else sol.array()
     if arr.shape != fw.us.shape:          # save_everystep with a different (noisy) step count
         assert noisy and kw.get("saveat") is None
@@ -94,7 +111,7 @@ def node_case(chain, mlp, p, u0, tspan, kw, dL_fn=None, augment=0, noisy=False, 
         np.testing.assert_allclose(np.asarray(sol.t), fw.ts, rtol=1e-6, atol=1e-7)
         close(arr, fw.us, rtol=rtol, what="states")
     du0, dp = back(dL[:, 0, :] if vec else dL)
-    check_steps(layer.last["adjoint_stats"], adj.stats, "adjoint", adj_exact and not noisy)
+    check_steps(layer.last["adjoint_stats"], adj.stats, "adjoint", adj_exact and not noisy, spread_a)
     if every and not noisy:
         rtol = max(rtol, 1e-3)
     if not (noisy and every):
@@ -318,8 +335,14 @@ def test_tensor_core_engine_rejects_ineligible_shapes():
 @pytest.mark.parametrize("sense", [1, 0])
 def test_tensor_core_engine_adjoint(sense):
     """tcgen05 adjoint (forward recompute + dgrad + MN-major wgrad GEMMs, opts.path = 2) against the oracle
-    and the FP32-FFMA kernels at the headline shape: gradients within rtol 1e-4, same forward steps."""
+    and the FP32-FFMA kernels at the headline shape: states and gradients element-wise within rtol 1e-4.
+    The oracle accumulates the parameter gradient in the CUDA path's order (per 128-trajectory tile, tiles in fp64).
+    Step counts: forward exact on FFMA and within 1 on the tensor cores; the adjoint's first ~15 steps ramp dt up
+    from Hairer's tiny first step (mu(t1) = 0 against abstol 1e-6) with an error estimate that is pure rounding
+    noise, so its count follows the arithmetic's noise floor: FFMA within 1 of the oracle,
+    tensor cores within 8 %."""
     rng, mlp, p, chain = make([64, 256, 256, 64], 3, scale=2.5)
+    mlp.wgrad_accum = ("tile_defer", 128)
     B = 200                                                    # ragged: 1 full + 1 partial 128-row tile
     u0 = rng.standard_normal((B, 64)).astype(np.float32)
     sa = dfx.BacksolveAdjoint() if sense else dfx.InterpolatingAdjoint()
@@ -338,9 +361,140 @@ def test_tensor_core_engine_adjoint(sense):
         ast = node.last["adjoint_stats"]
         assert sol.stats.engine == path - 1 and ast.engine == path - 1
         assert abs(sol.stats.naccept - fw.stats.naccept) <= (0 if path == 1 else 1), "forward steps"
-        check_steps(ast, adj.stats, f"adjoint path {path}", False)
+        assert sol.stats.nreject == fw.stats.nreject and ast.nreject == adj.stats.nreject
+        lim = 1 if path == 1 else max(2, -(-8 * adj.stats.naccept // 100))
+        assert abs(ast.naccept - adj.stats.naccept) <= lim, f"adjoint steps path {path}: {counts(ast)} vs oracle {counts(adj.stats)}"
+        assert ast.nf == 3 + 6 * (ast.naccept + ast.nreject) + (0 if sense else 1)      # FSAL + one re-evaluation per interior jump
         close(sol.array(), fw.us, what=f"states path {path}")
         close(dp, adj.dp, what=f"dp path {path}")
         close(du0, adj.du0, what=f"du0 path {path}")
         out[path] = (du0, dp)
     close(out[2][1], out[1][1], rtol=1e-4, what="dp tensor-core vs FFMA")
+
+
+@pytest.mark.parametrize("sense", [0, 1])
+def test_augmented_node_tight_tolerance(sense):
+    """AugmentedNDELayer (src/neural_de.jl:372-386) at abstol = reltol = 1e-6 with interior loss jumps: forward step
+    count exact, states / dp / d(input) element-wise within rtol 1e-4 (observed ~2e-6); no gradient reaches the
+    zero-padded rows.  (The adjoint count is not compared: see test_tensor_core_engine_adjoint.)"""
+    rng, mlp, p, chain = make([8, 64, 8], 5, scale=3.0)
+    u0 = rng.standard_normal((256, 6)).astype(np.float32)
+    sa = dfx.BacksolveAdjoint() if sense else dfx.InterpolatingAdjoint()
+    kw = dict(abstol=1e-6, reltol=1e-6, saveat=[0.25, 0.5, 1.0], sensealg=sa)
+    okw = {k: v for k, v in kw.items() if k != "sensealg"}
+    prob = onode.NodeProblem(mlp)
+    fw = onode.forward(prob, p, u0, 0.0, 1.0, dense=(sense == 0), augment=2, **okw)
+    dL = np.sin(np.arange(fw.us.size, dtype=np.float32).reshape(fw.us.shape) * 0.37)
+    adj = onode.adjoint(prob, p, fw, dL, sensealg=sense, augment=2, abstol=1e-6, reltol=1e-6)
+    layer = dfx.AugmentedNDELayer(dfx.NeuralODE(chain, (0.0, 1.0), dfx.Tsit5(), **kw), 2)
+    sol, back = layer.pullback(u0, p)
+    du0, dp = back(dL)
+    check_steps(sol.stats, fw.stats, "forward", True)
+    assert fw.stats.tie_dist > 0.5                     # truncation-dominated: no accept/reject decision near a tie
+    assert sol.array().shape == (3, 256, 8) and du0.shape == (256, 6)
+    close(sol.array(), fw.us, what="states")
+    close(dp, adj.dp, what="dp")
+    close(du0, adj.du0, what="du0")
+
+
+def test_ffjord_gradients_large_batch():
+    """FFJORD (src/ffjord.jl:81-178, monte-carlo branch) at B = 4096 with fresh Hutchinson noise per RHS call: step
+    counts of both passes exact (rejected steps included), logpx and d(x) element-wise within 1e-4 and the parameter
+    gradient within 1e-4 (it is a sum over 4096 trajectories of second-order terms; observed 4e-5)."""
+    rng = np.random.default_rng(6)
+    mlp = MLP([2, 16, 16, 2], [ACT_TANH, ACT_TANH, ACT_ID])
+    p = mlp.init(rng, scale=0.5)
+    B = 4096
+    x = rng.standard_normal((B, 2)).astype(np.float32)
+    tol = dict(abstol=1e-3, reltol=1e-3)
+    prob = onode.FfjordProblem(mlp, seed=3)
+    fw = onode.forward(prob, p, np.concatenate([x, np.zeros((B, 1), np.float32)], 1), 0.0, 0.5, save_everystep=False,
+                       save_start=False, dense=True, **tol)
+    g = np.full(B, -1.0 / B, np.float32)
+    adj = onode.adjoint(prob, p, fw, onode.ffjord_logpx_grad(fw.us[0], 2, g)[None], **tol)
+    chain = dfx.Chain(dfx.Dense(2, 16, dfx.tanh), dfx.Dense(16, 16, dfx.tanh), dfx.Dense(16, 2))
+    ff = dfx.FFJORD(chain, (0.0, 0.5), (2,), dfx.Tsit5(), **tol)
+    logpx, back = ff.pullback(x, p, {"regularize": False, "monte_carlo": True, "seed": 3, "calls": 0})
+    dx, dp = back(g)
+    check_steps(ff.last["stats"], fw.stats, "ffjord forward", True)
+    check_steps(ff.last["adjoint_stats"], adj.stats, "ffjord adjoint", True)
+    assert fw.stats.nreject > 0
+    close(np.asarray(logpx).reshape(-1), onode.ffjord_logpx(fw.us[0], 2), what="logpx")
+    close(dx, adj.du0[:, :2], what="dx")
+    close(dp, adj.dp, what="dp")
+
+
+def test_multiple_shoot_data_gradient():
+    """b200_mshoot_adjoint's d_data blocks ([G][B][D], one per group, accumulated at time index first[g]): with a loss
+    that reads only the predictions and no continuity term, d(loss)/d(ode_data) is exactly the groups' initial-
+    condition cotangents, which the NeuralODE pullback of each group returns independently."""
+    import torch
+    rng, mlp, p, chain = make([4, 16, 4], 7, scale=2.0)
+    ts = np.linspace(0, 2, 9, dtype=np.float32)
+    data = rng.standard_normal((9, 24, 4)).astype(np.float32)
+    tol = dict(abstol=1e-6, reltol=1e-6)
+    pt = torch.tensor(p, requires_grad=True)
+    dt = torch.tensor(data, requires_grad=True)
+    prob = dfx.ODEProblem(chain, data[0], (0.0, 2.0), p)
+    loss, preds = dfx.multiple_shoot(pt, dt, ts, prob, lambda u, uh: (uh ** 2).sum(), dfx.Tsit5(), 3, continuity_term=0, **tol)
+    loss.backward()
+    want = np.zeros_like(data)
+    dp_want = np.zeros_like(p)
+    for (a, b), pr in zip(dfx.group_ranges(9, 3), preds):
+        node = dfx.NeuralODE(chain, (float(ts[a]), float(ts[b])), dfx.Tsit5(), saveat=ts[a:b + 1], **tol)
+        sol, back = node.pullback(data[a], p)
+        close(sol.array(), pr.detach().numpy(), rtol=1e-6, what="group prediction")
+        du0, dpg = back(2 * sol.array())
+        want[a] += du0
+        dp_want += dpg
+    close(dt.grad.numpy(), want, rtol=1e-5, what="d(ode_data)")
+    close(pt.grad.numpy(), dp_want, rtol=1e-5, what="dp")
+    assert np.abs(want[[0, 2, 4, 6]]).max() > 0 and np.abs(want[[1, 3, 5, 7, 8]]).max() == 0
+
+
+def test_wide_model_picks_a_tile_that_fits_beside_the_static_shared_memory():
+    """the tile planner must budget the kernel's static __shared__ block (21 KB) beside the dynamic
+    part.  128 -> 768 -> 768 -> 128 needs 229 KB of dynamic shared memory for 32-row tiles, which passes a naive
+    "opt-in minus 2 KB" check and then fails at launch; the planner now falls back to 16-row tiles."""
+    rng, mlp, p, chain = make([128, 768, 768, 128], 9, scale=1.0)
+    u0 = rng.standard_normal((48, 128)).astype(np.float32)
+    kw = dict(abstol=1e-4, reltol=1e-4, save_everystep=False, save_start=False, sensealg=dfx.BacksolveAdjoint())
+    node = dfx.NeuralODE(chain, (0.0, 0.5), dfx.Tsit5(), **kw)
+    sol, back = node.pullback(u0, p)
+    du0, dp = back(np.ones_like(sol.array()))
+    assert sol.retcode == 0 and node.last["adjoint_stats"].tile in (8, 16)
+    prob = onode.NodeProblem(mlp)
+    fw = onode.forward(prob, p, u0, 0.0, 0.5, abstol=1e-4, reltol=1e-4, save_everystep=False, save_start=False)
+    adj = onode.adjoint(prob, p, fw, np.ones_like(fw.us), sensealg=1, abstol=1e-4, reltol=1e-4)
+    close(sol.array(), fw.us, rtol=3e-4, what="states")
+    close(dp, adj.dp, rtol=3e-4, what="dp")
+
+
+def test_c_abi_argument_errors_and_tape_ownership():
+    """save_everystep without a tape is an argument error (it used to return success with untouched outputs); a
+    tape outlives its context safely; the scalar saveat of a reversed time span is t0:-h:t1."""
+    import ctypes as C
+    from diffeqflux_jl_b200 import _native as N
+    from diffeqflux_jl_b200 import layers
+    lib = N.lib()
+    ctx = N.Context(0)
+    dims, acts = (C.c_int * 3)(2, 8, 2), (C.c_int * 2)(N.ACT_TANH, N.ACT_IDENTITY)
+    mh = C.c_void_p()
+    assert lib.b200_model_create(ctx._h, 2, dims, acts, 0, C.byref(mh)) == 0
+    p = np.zeros(lib.b200_model_nparams(mh), np.float32)
+    u0 = np.ones((3, 2), np.float32)
+    o = N.default_opts()
+    o.save_everystep = 1
+    st = N.Stats()
+    rc = lib.b200_node_forward(ctx._h, mh, p.ctypes.data, u0.ctypes.data, 2, 0, 3, 0.0, 1.0, None, 0, C.byref(o), None, None, C.byref(st), None)
+    assert rc == -1 and b"tape" in lib.b200_last_error(ctx._h)
+    tape = C.c_void_p()
+    rc = lib.b200_node_forward(ctx._h, mh, p.ctypes.data, u0.ctypes.data, 2, 0, 3, 0.0, 1.0, None, 0, C.byref(o), None, None, C.byref(st), C.byref(tape))
+    assert rc == 0 and tape.value and lib.b200_tape_nsteps(tape) == st.naccept
+    other = N.Context(0)
+    assert lib.b200_tape_steps(other._h, tape, None, None, 0) == -1          # a tape is bound to the context that recorded it
+    ctx.close()                                                              # context first ...
+    lib.b200_tape_free(tape)                                                 # ... then the tape: must not touch freed memory
+    other.close()
+    iv, ss, se, sev = layers._split_saveat(0.25, 1.0, 0.0, None, None, None)
+    assert np.allclose(iv, [0.75, 0.5, 0.25]) and ss and se and not sev
