@@ -93,6 +93,10 @@ _SIGNATURES = {
                                       C.POINTER(Opts), _fp, C.POINTER(Stats), C.POINTER(_vp)]),
     "b200_mshoot_adjoint": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.c_int, _fp, C.POINTER(Opts), _fp, _fp,
                                       C.POINTER(Stats)]),
+    "b200_node_train_step": (C.c_int, [_vp, _vp, _fp, _fp, _fp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _fp,
+                                       C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp, C.c_int, _fp, C.POINTER(Opts),
+                                       _fp, C.POINTER(Stats), C.POINTER(Stats)]),
+    "b200_dimmover": (C.c_int, [_vp, _fp, C.c_int, _ip, C.c_int, C.c_int, _fp, _ip, _ip, C.c_int]),
     "b200_ctx_ipc_export": (C.c_int, [_vp, C.c_char_p]),
     "b200_ctx_ipc_import": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p]),
 }

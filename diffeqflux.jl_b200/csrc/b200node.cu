@@ -416,6 +416,62 @@ __global__ void extract_cols_kernel(const float* __restrict__ src, int B, int NV
   dst[i] = accumulate ? dst[i] + v : v;
 }
 
+// sum-of-squares loss against the data and its cotangent: loss = sum (pred - data)^2, dL = 2 (pred - data)
+// (docs/src/examples/neural_ode.md:36-44 `loss = sum(abs2, ode_data .- pred)`); fp64 partial per block, fixed order
+__global__ void sse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ data, long long n,
+                                float* __restrict__ dL, double* __restrict__ partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = pred[i] - data[i];
+    dL[i] = 2.f * d;
+    acc += (double)d * (double)d;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int n, float* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    *out = (float)s;
+  }
+}
+// Optimisers.jl Adam (OptimizationOptimisers.Adam, docs/src/examples/neural_ode.md:70):
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr * (m / (1 - b1^t)) / (sqrt(v / (1 - b2^t)) + eps)
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ g, int n, float lr, float b1, float b2, float eps, float c1, float c2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+}
+// general strided gather used by b200_dimmover: out (contiguous, <= 5 axes, axis 0 fastest) <- in[sum idx_a * stride_a]
+struct PermDesc { int nd; long long dim[5]; long long stride[5]; };
+__global__ void strided_copy_kernel(PermDesc d, const float* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i, off = 0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      if (a < d.nd) {
+        const long long q = r / d.dim[a];
+        off += (r - q * d.dim[a]) * d.stride[a];
+        r = q;
+      }
+    }
+    out[i] = in[off];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ planning
 static int plan_smem(const MlpDesc& m, int flavor, int TB, SmemPlan& sp) {
   memset(&sp, 0, sizeof sp);
@@ -1252,6 +1308,128 @@ extern "C" int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_
   cudaStreamSynchronize(ctx->stream);
   free_temps(ctx, temps);
   return rc < 0 ? rc : worst;
+}
+
+// ------------------------------------------------------------------------------------------------ training step / output helpers
+extern "C" int b200_node_train_step(b200_ctx* ctx, const b200_model* model, float* p, float* adam_m, float* adam_v,
+                                    int step, float lr, float beta1, float beta2, float eps, const float* u0, int d_in,
+                                    int augment, int B, float t0, float t1, const float* saveat, int nsave,
+                                    const float* data, const b200_opts* o, float* loss, b200_stats* fwd_stats,
+                                    b200_stats* adj_stats) {
+  int rc = check_common(ctx, model, o, B);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const MlpDesc& m = model->m;
+  if (!p || !adam_m || !adam_v || !u0 || !data) return set_err(ctx, B200_ERR_ARG, "null p/adam state/u0/data");
+  if (step < 1 || !(lr > 0.f)) return set_err(ctx, B200_ERR_ARG, "step must be >= 1 and lr > 0");
+  if (d_in < 1 || augment < 0 || d_in + augment != m.dims[0]) return set_err(ctx, B200_ERR_ARG, "state size mismatch");
+  if (o->sensealg != B200_SENSE_INTERPOLATING && o->sensealg != B200_SENSE_BACKSOLVE) return set_err(ctx, B200_ERR_ARG, "sensealg");
+  if (o->save_everystep) return set_err(ctx, B200_ERR_UNSUPPORTED, "train step needs saveat / the end state (save_everystep = 0)");
+  const int n_out = (o->save_start ? 1 : 0) + nsave + (o->save_end ? 1 : 0);
+  if (n_out < 1) return set_err(ctx, B200_ERR_ARG, "no saved point to compare with the data");
+  const int D = m.dims[0];
+  const size_t nsaved = (size_t)n_out * B * D;
+  std::vector<void*> temps;
+  const bool host = o->ptr_kind == B200_PTR_HOST;
+  float *p_d = p, *m_d = adam_m, *v_d = adam_v;
+  const float *u0_d, *sv_d, *data_d;
+  cudaError_t e = cudaSuccess;
+  if (host) {
+    for (float** q : {&p_d, &m_d, &v_d}) {
+      float* src = *q;
+      CU(dalloc(ctx, q, (size_t)m.nparams));
+      temps.push_back(*q);
+      CU(cudaMemcpyAsync(*q, src, m.nparams * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  if ((rc = to_device(ctx, u0, (size_t)B * d_in, o->ptr_kind, &u0_d, temps))) return rc;
+  if ((rc = to_device(ctx, saveat, (size_t)nsave, o->ptr_kind, &sv_d, temps))) return rc;
+  if ((rc = to_device(ctx, data, nsaved, o->ptr_kind, &data_d, temps))) return rc;
+  b200_tape* t = nullptr;
+  rc = forward_core(ctx, model, FL_FWD_NODE, p_d, u0_d, d_in, augment, B, t0, t1, sv_d, nsave, o, fwd_stats, &t);
+  if (rc != 0) {                                  // error, or a retcode other than Success: no update (the caller sees the code)
+    if (t) b200_tape_free(t);
+    free_temps(ctx, temps);
+    return rc;
+  }
+  float *dL = nullptr, *loss_d = nullptr;
+  double* partial = nullptr;
+  const int nblk = 296;
+  e = dalloc(ctx, &dL, nsaved);
+  if (e == cudaSuccess) e = dalloc(ctx, &loss_d, 1);
+  if (e == cudaSuccess) e = dalloc(ctx, &partial, (size_t)nblk);
+  if (e != cudaSuccess) { b200_tape_free(t); free_temps(ctx, temps); return set_err(ctx, B200_ERR_CUDA, "train step workspace: %s", cudaGetErrorString(e)); }
+  temps.push_back(dL); temps.push_back(loss_d); temps.push_back(partial);
+  sse_loss_kernel<<<nblk, 256, 0, ctx->stream>>>(t->out_u, data_d, (long long)nsaved, dL, partial);
+  sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(partial, nblk, loss_d);
+  const int flavor = o->sensealg == B200_SENSE_INTERPOLATING ? FL_ADJ_NODE_INTERP : FL_ADJ_NODE_BACKSOLVE;
+  float *lam = nullptr, *mu = nullptr;
+  rc = adjoint_core(ctx, t, flavor, dL, o, &lam, &mu, adj_stats);
+  if (rc == 0) {
+    float* g = nullptr;
+    e = dalloc(ctx, &g, (size_t)m.nparams);
+    if (e == cudaSuccess) {
+      temps.push_back(g);
+      unpack_grad_kernel<<<dim3(32, m.nl), 256, 0, ctx->stream>>>(m, mu, g, 0);
+      const float c1 = 1.f - powf(beta1, (float)step), c2 = 1.f - powf(beta2, (float)step);
+      adam_kernel<<<(m.nparams + 255) / 256, 256, 0, ctx->stream>>>(p_d, m_d, v_d, g, m.nparams, lr, beta1, beta2, eps, c1, c2);
+      if (host) {
+        from_device(ctx, p, p_d, (size_t)m.nparams, B200_PTR_HOST);
+        from_device(ctx, adam_m, m_d, (size_t)m.nparams, B200_PTR_HOST);
+        from_device(ctx, adam_v, v_d, (size_t)m.nparams, B200_PTR_HOST);
+      }
+    } else rc = set_err(ctx, B200_ERR_CUDA, "train step gradient buffer: %s", cudaGetErrorString(e));
+  }
+  if (rc >= 0 && loss) from_device(ctx, loss, loss_d, 1, o->ptr_kind);
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess && rc >= 0) rc = set_err(ctx, B200_ERR_CUDA, "train step: %s", cudaGetErrorString(e));
+  dfree(ctx, lam);
+  dfree(ctx, mu);
+  b200_tape_free(t);
+  free_temps(ctx, temps);
+  return rc;
+}
+
+extern "C" int b200_dimmover(b200_ctx* ctx, const float* x, int ndims, const int* dims, int from, int to, float* out,
+                             int* out_ndims, int* out_dims, int ptr_kind) {
+  if (!ctx) return B200_ERR_ARG;
+  if (!x || !out || !dims || ndims < 2 || ndims > 4) return set_err(ctx, B200_ERR_ARG, "dimmover: 2 <= ndims <= 4 and non-null buffers");
+  if (from == 0 || to == 0) return set_err(ctx, B200_ERR_ARG, "dimmover: from and to must be non-zero (src/neural_de.jl:407)");
+  const int f = (from > 0 ? from : ndims + 1 + from) - 1, tt = (to > 0 ? to : ndims + 1 + to) - 1;   // 0-based (Julia order)
+  if (f < 0 || f >= ndims || tt < 0 || tt >= ndims) return set_err(ctx, B200_ERR_ARG, "dimmover: from/to out of range");
+  DeviceGuard guard(ctx->device);
+  // Julia column-major strides of x
+  long long st[4], n = 1;
+  for (int a = 0; a < ndims; ++a) { st[a] = n; n *= dims[a]; }
+  // slices drop axis f; cat(...; dims = to): to == ndims (1-based) appends a new axis, otherwise it concatenates along
+  // axis `to` of the (ndims-1)-dimensional slices
+  PermDesc d{};
+  int sl[3], nsl = 0;
+  for (int a = 0; a < ndims; ++a) if (a != f) sl[nsl++] = a;
+  int od[4], ond = 0;
+  if (tt == ndims - 1) {
+    for (int k = 0; k < nsl; ++k) { d.dim[d.nd] = dims[sl[k]]; d.stride[d.nd++] = st[sl[k]]; od[ond++] = dims[sl[k]]; }
+    d.dim[d.nd] = dims[f]; d.stride[d.nd++] = st[f]; od[ond++] = dims[f];
+  } else {
+    for (int k = 0; k < nsl; ++k) {
+      d.dim[d.nd] = dims[sl[k]]; d.stride[d.nd++] = st[sl[k]];
+      if (k == tt) { d.dim[d.nd] = dims[f]; d.stride[d.nd++] = st[f]; od[ond++] = dims[sl[k]] * dims[f]; }
+      else od[ond++] = dims[sl[k]];
+    }
+  }
+  if (out_ndims) *out_ndims = ond;
+  if (out_dims) for (int a = 0; a < ond; ++a) out_dims[a] = od[a];
+  std::vector<void*> temps;
+  const float* x_d;
+  int rc = to_device(ctx, x, (size_t)n, ptr_kind, &x_d, temps);
+  if (rc) return rc;
+  float* o_d = out;
+  if (ptr_kind == B200_PTR_HOST) { CU(dalloc(ctx, &o_d, (size_t)n)); temps.push_back(o_d); }
+  strided_copy_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(d, x_d, o_d, n);
+  if (ptr_kind == B200_PTR_HOST) from_device(ctx, out, o_d, (size_t)n, B200_PTR_HOST);
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_temps(ctx, temps);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ multi-GPU plumbing

@@ -647,6 +647,141 @@ class FFJORD:
         return fw["logpx"], back
 
 
+    def backward(self, n_samples: int, ps, st, rng=None, z=None):
+        """`__backward_ffjord(T, n, n_samples, ps, st, rng)` (src/ffjord.jl:183-214): draw z ~ N(0, I) (or take `z`),
+        integrate the same augmented RHS over reverse(tspan) and return the first D rows of the end state -- samples of
+        the learned density.  One b200_ffjord_forward call with the time span reversed."""
+        if st.get("regularize", False):
+            raise UnsupportedError("regularize = true is outside the B200 path")
+        if not st.get("monte_carlo", True):
+            raise UnsupportedError("monte_carlo = false (exact trace) is outside the B200 path")
+        D = self.model.dims[0]
+        if z is None:
+            rng = np.random.default_rng() if rng is None else rng
+            z = rng.standard_normal((int(n_samples), D)).astype(np.float32)
+            if _is_torch(ps):
+                z = torch.from_numpy(z).to(ps.device)
+        seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
+        rev = FFJORD(self.model, (self.tspan[1], self.tspan[0]), self.input_dims, *self.args, **self.kwargs)
+        fw = rev._forward(z, ps, seed, want_tape=False)
+        self.last = fw
+        return fw["z"][:, :D]
+
+
+class FFJORDDistribution:
+    """`FFJORDDistribution(model, ps, st)` (src/ffjord.jl:215-245): `logpdf(d, x)` = first output of the forward pass,
+    `rand(rng, d, n)` = `__backward_ffjord`."""
+
+    def __init__(self, model: FFJORD, ps, st):
+        self.model, self.ps, self.st = model, ps, st
+
+    def __len__(self):
+        return int(np.prod(self.model.input_dims))
+
+    def logpdf(self, x):
+        x2 = x.reshape(1, -1) if (x.dim() if _is_torch(x) else np.asarray(x).ndim) == 1 else x
+        (logpx, _, _), _ = self.model(x2, self.ps, self.st)
+        return logpx.reshape(-1)
+
+    def rand(self, n: int = 1, rng=None):
+        return self.model.backward(n, self.ps, self.st, rng)
+
+
+# --------------------------------------------------------------------------------------- training step / DimMover
+@dataclass
+class AdamState:
+    """State of `OptimizationOptimisers.Adam(lr)` (Optimisers.jl defaults beta = (0.9, 0.999), eps = 1e-8)."""
+    lr: float = 0.05
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    step: int = 0
+    m: object = None
+    v: object = None
+
+
+def train_step(node: "NeuralODE", u0, p, data, opt: AdamState):
+    """One iteration of the docs' training loop (docs/src/examples/neural_ode.md:36-44,64-70) as ONE C-ABI call
+    (b200_node_train_step): forward solve at the layer's saveat, loss = sum(abs2, data .- pred), adjoint gradient and the
+    Adam update of `p` IN PLACE.  Returns (loss before the update, retcode).  With CUDA tensors nothing but the loss
+    scalar leaves the device."""
+    solve = node._solve
+    t0, t1 = solve.tspan
+    xb, pb, db = _Buf(u0), _Buf(p), _Buf(data)
+    if not (xb.dev == pb.dev == db.dev):
+        raise ValueError("u0, p and data must live on the same device")
+    if not _is_torch(p) and not (isinstance(p, np.ndarray) and p.dtype == np.float32 and p.flags.c_contiguous):
+        raise ValueError("p is updated in place: pass a contiguous float32 array / tensor")
+    if _is_torch(p) and not p.is_contiguous():
+        raise ValueError("p is updated in place: pass a contiguous tensor")
+    vec = (xb.t.dim() if _is_torch(u0) else xb.a.ndim) == 1
+    shape = tuple(xb.t.shape) if _is_torch(u0) else xb.a.shape
+    B, d_in = (1, shape[0]) if vec else shape
+    on_dev = xb.dev
+    dev = _pick_device(u0, p)
+    ctx = _context(dev)
+    mh = _model_handle(ctx, solve.chain)
+    interior, ss, se, sev = _split_saveat(solve.kw.get("saveat"), t0, t1, solve.kw.get("save_start"), solve.kw.get("save_end"),
+                                          solve.kw.get("save_everystep"))
+    if sev:
+        raise UnsupportedError("train_step needs saveat (or save_everystep = false): the data must have a fixed time grid")
+    o = solve.opts(on_dev, True)
+    o.save_start, o.save_end, o.save_everystep = int(ss), int(se), 0
+    n_out = int(ss) + len(interior) + int(se)
+    D = d_in + solve.augment
+    dshape = tuple(db.t.shape) if _is_torch(data) else db.a.shape
+    if int(np.prod(dshape)) != n_out * B * D:
+        raise ValueError(f"DimensionMismatch: data has {int(np.prod(dshape))} entries, the prediction {n_out} x {B} x {D}")
+    nP = solve.chain.nparams
+    if opt.m is None:
+        opt.m = torch.zeros(nP, dtype=torch.float32, device=p.device) if _is_torch(p) else np.zeros(nP, np.float32)
+        opt.v = torch.zeros(nP, dtype=torch.float32, device=p.device) if _is_torch(p) else np.zeros(nP, np.float32)
+    opt.step += 1
+    if on_dev:
+        sv_t = torch.from_numpy(interior).to(f"cuda:{dev}") if interior.size else None
+        sv_ptr = sv_t.data_ptr() if sv_t is not None else None
+    else:
+        sv_ptr = interior.ctypes.data if interior.size else None
+    loss = _alloc((1,), None, on_dev, dev)
+    fst, ast = N.Stats(), N.Stats()
+    rc = ctx.check(N.lib().b200_node_train_step(
+        ctx._h, mh, _ptr(p), _ptr(opt.m), _ptr(opt.v), opt.step, float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps),
+        xb.ptr, d_in, solve.augment, B, float(t0), float(t1), sv_ptr, len(interior), db.ptr, C.byref(o), _ptr(loss),
+        C.byref(fst), C.byref(ast)))
+    node.last = dict(stats=SolveStats(fst.nf, fst.naccept, fst.nreject, fst.kernel_ms, fst.tie_dist, fst.grid, fst.tile, fst.engine),
+                     adjoint_stats=SolveStats(ast.nf, ast.naccept, ast.nreject, ast.kernel_ms, ast.tie_dist, ast.grid, ast.tile, ast.engine), rc=rc)
+    return float(loss[0]), rc
+
+
+class DimMover:
+    """`DimMover(; from = -2, to = -1)` (src/neural_de.jl:397-412): `cat(eachslice(x; dims = from)...; dims = to)`.
+    Arrays here are the C-order views of Julia arrays (shape reversed: `Array(sol)` (D,B,T) is (T,B,D)), and the layer
+    returns the C-order view of the Julia result, so the default turns (T,B,D) into (B,T,D).  Runs on the device
+    through b200_dimmover."""
+
+    def __init__(self, from_: int = -2, to: int = -1, **kw):
+        from_ = kw.pop("from", from_)
+        if kw:
+            raise TypeError(f"unexpected keyword(s) {sorted(kw)}")
+        if from_ == 0 or to == 0:
+            raise AssertionError("from !== 0 && to !== 0")
+        self.from_, self.to = int(from_), int(to)
+
+    def __call__(self, x, ps=None, st=None):
+        xb = _Buf(x)
+        shape = tuple(xb.t.shape) if _is_torch(x) else xb.a.shape
+        nd = len(shape)
+        jdims = (C.c_int * nd)(*shape[::-1])                     # Julia dimension order
+        dev = _pick_device(x)
+        ctx = _context(dev)
+        ond, odims = C.c_int(), (C.c_int * 4)()
+        out = _alloc((int(np.prod(shape)),), None, xb.dev, dev)
+        ctx.check(N.lib().b200_dimmover(ctx._h, xb.ptr, nd, jdims, self.from_, self.to, _ptr(out), C.byref(ond), odims,
+                                        N.PTR_DEVICE if xb.dev else N.PTR_HOST))
+        oshape = tuple(odims[i] for i in range(ond.value))[::-1]
+        return out.reshape(oshape), ({} if st is None else st)
+
+
 # --------------------------------------------------------------------------------------- multiple shooting
 def group_ranges(datasize: int, groupsize: int):
     """`group_ranges(datasize, groupsize)` (src/multiple_shooting.jl:231-239) as 0-based inclusive

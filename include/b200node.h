@@ -184,6 +184,27 @@ int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_tape** tape
                         const float* dL_dpreds, const b200_opts* opts, float* dp, float* d_data,
                         b200_stats* stats);
 
+/* ---- the caller's side of the path: one training iteration, output re-layout ------------------- */
+/* One iteration of the docs' training loop (docs/src/examples/neural_ode.md:36-44,64-70:
+ * `loss = sum(abs2, ode_data .- Array(prob_neuralode(u0, p, st)[1]))`, Zygote gradient, `OptimizationOptimisers.Adam(lr)`)
+ * in ONE call, everything on the device: forward solve with saveat, loss and dL/du(t_i) = 2 (pred - data), adjoint,
+ * Adam update of p in place.  With opts->ptr_kind == B200_PTR_DEVICE p / adam_m / adam_v stay resident in HBM across
+ * iterations (no D*B*T host round trip per iteration).
+ *   p, adam_m, adam_v [P] in/out (m = v = 0 before step 1);  step: 1-based iteration number (bias correction);
+ *   data [n_out][B][D] laid out like out_u of b200_node_forward;  loss: receives the loss BEFORE the update.
+ * A retcode other than Success returns without touching p (the reference's loop would see an Inf/NaN loss). */
+int b200_node_train_step(b200_ctx* ctx, const b200_model* model, float* p, float* adam_m, float* adam_v, int step,
+                         float lr, float beta1, float beta2, float eps, const float* u0, int d_in, int augment, int B,
+                         float t0, float t1, const float* saveat, int nsave, const float* data,
+                         const b200_opts* opts, float* loss, b200_stats* fwd_stats, b200_stats* adj_stats);
+
+/* `DimMover(from, to)` (src/neural_de.jl:397-412): `cat(eachslice(x; dims = from)...; dims = to)` on the device.
+ * x is a Julia column-major array of `ndims` (2..4) dimensions `dims` (so `Array(sol)` (D,B,T) is dims = {D,B,T});
+ * from / to are 1-based, negative values count from the end (defaults of the reference: from = -2, to = -1, which
+ * turns (D,B,T) into (D,T,B)).  out receives the same number of elements; out_ndims / out_dims the result shape. */
+int b200_dimmover(b200_ctx* ctx, const float* x, int ndims, const int* dims, int from, int to, float* out,
+                  int* out_ndims, int* out_dims, int ptr_kind);
+
 /* ---- multi-GPU (one process per GPU; handles travel over torch.distributed / MPI / files) ----- */
 /* Each rank exports a CUDA-IPC handle of its step mailbox, all-gathers the handles with its own
  * plumbing, and imports the peers'.  Afterwards every solve on this ctx shards the batch: the

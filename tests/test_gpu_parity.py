@@ -498,3 +498,68 @@ def test_c_abi_argument_errors_and_tape_ownership():
     other.close()
     iv, ss, se, sev = layers._split_saveat(0.25, 1.0, 0.0, None, None, None)
     assert np.allclose(iv, [0.75, 0.5, 0.25]) and ss and se and not sev
+
+
+def test_fused_training_step_matches_the_oracle_loop():
+    """N2: b200_node_train_step (forward + sum-of-squares loss + adjoint + Adam in one call, parameters and optimiser
+    state resident on the device) against the oracle's loop of docs/src/examples/neural_ode.md:36-70 for 4 iterations."""
+    import torch
+    from oracle import train as otrain
+    rng, mlp, p0, chain = make([2, 50, 2], 2, pre=True)
+    u0 = np.array([[2.0, 0.0]], np.float32)
+    ts = np.linspace(0, 1.5, 30, dtype=np.float32)
+    A = np.array([[-0.1, 2.0], [-2.0, -0.1]], np.float32)
+    data = np.zeros((30, 1, 2), np.float32)                        # a crude spiral-like target (any fixed data does)
+    for i, t in enumerate(ts):
+        data[i, 0] = 2.0 * np.exp(-0.1 * t) * np.array([np.cos(2 * t), -np.sin(2 * t)], np.float32)
+    prob = onode.NodeProblem(mlp)
+    node = dfx.NeuralODE(chain, (0.0, 1.5), dfx.Tsit5(), saveat=ts)
+    for device in ("host", "cuda"):
+        p_o, m_o, v_o = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+        if device == "cuda":
+            p_g, u_g, d_g = torch.tensor(p0).cuda(), torch.tensor(u0).cuda(), torch.tensor(data).cuda()
+        else:
+            p_g, u_g, d_g = p0.copy(), u0, data
+        opt = dfx.AdamState(lr=0.05)
+        solid = np.ones(p0.size, bool)
+        for it in range(1, 5):
+            loss_o, p_o, m_o, v_o, g_o = otrain.train_step(prob, p_o, u0, data, 0.0, 1.5, it, m_o, v_o, saveat=ts, lr=0.05)
+            loss_g, rc = dfx.train_step(node, u_g, p_g, d_g, opt)
+            assert rc == 0 and abs(loss_g - loss_o) <= 3e-3 * abs(loss_o), (device, it, loss_g, loss_o)
+            pg = p_g.cpu().numpy() if device == "cuda" else p_g
+            # Adam normalises the gradient (each parameter moves by ~lr per step whatever the size of its gradient), so
+            # parameters whose gradient is numerically zero are ill-conditioned (lr * g / (|g| + 1e-8)); the others must
+            # agree to a fraction of lr between two valid fp32 gradient evaluations (rtol 3e-3 at reltol 1e-3)
+            solid &= np.abs(g_o) > 1e-3 * np.abs(g_o).max()
+            assert solid.sum() > p0.size // 3
+            assert np.abs(pg - p_o)[solid].max() <= 0.05 * 0.05 * it, (device, it, np.abs(pg - p_o)[solid].max())
+        assert opt.step == 4 and np.abs(pg - p0).max() > 0.05
+
+
+def test_dimmover_and_ffjord_sampling():
+    """N3 / N4: DimMover (src/neural_de.jl:397-412) on the device against the oracle's eachslice/cat, and
+    `__backward_ffjord` (src/ffjord.jl:183-214): the reverse-time flow of the forward flow's end points returns the data."""
+    import torch
+    from oracle import train as otrain
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((5, 7, 3)).astype(np.float32)            # C-order view of a Julia (3, 7, 5) = (D, B, T) array
+    xj = np.transpose(x, (2, 1, 0))
+    for frm, to in ((-2, -1), (1, 3), (3, 1), (2, 2), (-1, 1)):
+        want = np.transpose(otrain.dimmover(xj, frm, to))           # back to the C-order view
+        for arr in (x, torch.tensor(x).cuda()):
+            got, _ = dfx.DimMover(frm, to)(arr, None, {})
+            got = got.cpu().numpy() if hasattr(got, "cpu") else got
+            assert got.shape == want.shape and np.array_equal(got, want), (frm, to, got.shape, want.shape)
+    y, _ = dfx.DimMover()(x, None, {})
+    assert y.shape == (7, 5, 3) and np.array_equal(y, np.transpose(x, (1, 0, 2)))
+    # sampling: z = flow(x) forward, then flow^-1(z) through backward() must return x (noise does not enter the z rows)
+    rng2, mlp, p, chain = make([2, 16, 16, 2], 6, scale=0.5)
+    xs = rng2.standard_normal((512, 2)).astype(np.float32)
+    ff = dfx.FFJORD(chain, (0.0, 0.5), (2,), dfx.Tsit5(), abstol=1e-6, reltol=1e-6, noise_per_call=0)
+    st = {"regularize": False, "monte_carlo": True, "seed": 3, "calls": 0}
+    ff(xs, p, st)
+    z = ff.last["z"][:, :2].copy()
+    back = ff.backward(512, p, st, z=z)
+    close(back, xs, rtol=1e-4, what="flow^-1(flow(x))")
+    d = dfx.FFJORDDistribution(ff, p, st)
+    assert len(d) == 2 and d.rand(64, np.random.default_rng(1)).shape == (64, 2) and d.logpdf(xs).shape == (512,)

@@ -280,3 +280,27 @@ def test_group_ranges_and_mshoot():
     lm, *_ = mshoot.multiple_shoot(prob, p - h * d, data, ts, 3, want_grad=False)
     fd = (lp - lm) / (2 * h)
     assert abs(float(dp @ d) - fd) < 2e-2 * max(1.0, abs(fd))
+
+
+def test_training_step_and_dimmover_restatement():
+    """oracle/train.py: Adam's first step moves every parameter by lr * sign(g) (bias-corrected m / sqrt(v) = +-1), the
+    loss decreases over a few iterations of the docs' loop, and DimMover reproduces Julia's eachslice/cat shapes."""
+    from oracle import train as otrain
+    g = np.array([0.5, -2.0, 1e-3], np.float32)
+    p, m, v = otrain.adam_update(np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32), g, 1, lr=0.05)
+    np.testing.assert_allclose(p, -0.05 * np.sign(g), rtol=1e-4)
+    x = np.arange(24, dtype=np.float32).reshape(2, 3, 4)                # Julia (2, 3, 4)
+    assert otrain.dimmover(x).shape == (2, 4, 3) and otrain.dimmover(x, 3, 1).shape == (8, 3) and otrain.dimmover(x, 2, 2).shape == (2, 12)
+    assert np.array_equal(otrain.dimmover(x)[:, :, 1], x[:, 1, :])
+    rng = np.random.default_rng(2)
+    mlp = MLP([2, 16, 2], [ACT_TANH, ACT_ID])
+    p = mlp.init(rng)
+    prob = node.NodeProblem(mlp)
+    ts = np.linspace(0, 1.0, 6, dtype=np.float32)
+    u0 = np.array([[1.0, 0.0]], np.float32)
+    data = np.stack([np.stack([np.cos(ts), -np.sin(ts)], -1)], 1).astype(np.float32)
+    m, v, losses = np.zeros_like(p), np.zeros_like(p), []
+    for it in range(1, 6):
+        loss, p, m, v, _ = otrain.train_step(prob, p, u0, data, 0.0, 1.0, it, m, v, saveat=ts, lr=0.05)
+        losses.append(loss)
+    assert losses[-1] < losses[0]
