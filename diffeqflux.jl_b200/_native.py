@@ -62,7 +62,7 @@ SUCCESS, MAXITERS, DT_LESS_THAN_MIN, UNSTABLE = 0, 1, 2, 3
 RETCODE_NAMES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}
 ACT_IDENTITY, ACT_TANH, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS = range(5)
 PRE_NONE, PRE_CUBE = 0, 1
-SENSE_NONE, SENSE_INTERPOLATING, SENSE_BACKSOLVE = -1, 0, 1
+SENSE_NONE, SENSE_INTERPOLATING, SENSE_BACKSOLVE, SENSE_QUADRATURE, SENSE_GAUSS = -1, 0, 1, 2, 3
 PTR_HOST, PTR_DEVICE = 0, 1
 IPC_HANDLE_BYTES = 64
 

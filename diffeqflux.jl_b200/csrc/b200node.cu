@@ -703,7 +703,7 @@ static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, cons
   t->ctx = ctx; t->m = m; t->fwd_flavor = flavor; t->sensealg = o->sensealg;
   t->B = B; t->NS = NS; t->D = D; t->d_in = d_in; t->augment = augment; t->t0 = t0; t->t1 = t1;
   t->seed = o->seed; t->noise_per_call = o->noise_per_call; t->b_offset = o->b_offset;
-  t->dense = (o->sensealg == B200_SENSE_INTERPOLATING) || o->save_everystep;
+  t->dense = (o->sensealg == B200_SENSE_INTERPOLATING || o->sensealg == B200_SENSE_QUADRATURE || o->sensealg == B200_SENSE_GAUSS) || o->save_everystep;
   if (o->save_everystep) nsave = 0;
   t->vec_elems = (long long)B * NS;
   const int n_out = (o->save_start ? 1 : 0) + nsave + (o->save_end ? 1 : 0);
@@ -840,8 +840,8 @@ extern "C" int b200_node_forward(b200_ctx* ctx, const b200_model* model, const f
   if (d_in < 1 || augment < 0 || d_in + augment != m.dims[0])
     return set_err(ctx, B200_ERR_ARG, "state size mismatch: d_in %d + augment %d != model input %d", d_in, augment, m.dims[0]);
   if (nsave < 0 || (nsave > 0 && !saveat)) return set_err(ctx, B200_ERR_ARG, "saveat");
-  if (o->sensealg < B200_SENSE_NONE || o->sensealg > B200_SENSE_BACKSOLVE)
-    return set_err(ctx, B200_ERR_UNSUPPORTED, "sensealg %d (supported: InterpolatingAdjoint, BacksolveAdjoint)", o->sensealg);
+  if (o->sensealg < B200_SENSE_NONE || o->sensealg > B200_SENSE_GAUSS)
+    return set_err(ctx, B200_ERR_UNSUPPORTED, "sensealg %d (supported: Interpolating, Backsolve, Quadrature, Gauss adjoints)", o->sensealg);
   if (o->save_everystep && o->sensealg == B200_SENSE_BACKSOLVE)
     return set_err(ctx, B200_ERR_UNSUPPORTED, "save_everystep with BacksolveAdjoint: pass saveat, or use InterpolatingAdjoint");
   std::vector<void*> temps;
@@ -928,7 +928,10 @@ static int adjoint_core(b200_ctx* ctx, b200_tape* t, int flavor, const float* dL
 
   P.wp = t->wp; P.wtp = t->wtp;
   P.B = t->B; P.NV = NV; P.D = t->D; P.NS = NS;
-  P.n_norm = (long long)t->B * ctx->world * NV + m.nparams;
+  // Quadrature / Gauss adjoints: lambda is integrated on its own (mu is a quadrature of lambda^T df/dp, not a state of
+  // the adjoint ODE): the parameter-gradient block stays out of the error norm, so the step sequence is lambda's alone
+  P.mu_in_norm = (t->sensealg == B200_SENSE_QUADRATURE || t->sensealg == B200_SENSE_GAUSS) ? 0 : 1;
+  P.n_norm = (long long)t->B * ctx->world * NV + (P.mu_in_norm ? m.nparams : 0);
   P.t0 = t->t1; P.t1 = t->t0;          // integrate backwards
   P.abstol = o->abstol; P.reltol = o->reltol; P.dt0_user = o->dt0; P.maxiters = o->maxiters;
   P.ring = ring; P.nslots = 2; P.vec_elems = vec; P.k1_first = k1; P.final_state = fin;
@@ -954,9 +957,9 @@ extern "C" int b200_node_adjoint(b200_ctx* ctx, const b200_model* model, b200_ta
   if (!tape || !dL_du) return set_err(ctx, B200_ERR_ARG, "null tape/dL_du");
   if (tape->ctx != ctx) return set_err(ctx, B200_ERR_ARG, "tape belongs to another (or a destroyed) context");
   if (tape->fwd_flavor != FL_FWD_NODE) return set_err(ctx, B200_ERR_ARG, "tape was not recorded by b200_node_forward");
-  if (tape->sensealg != B200_SENSE_INTERPOLATING && tape->sensealg != B200_SENSE_BACKSOLVE)
+  if (tape->sensealg < B200_SENSE_INTERPOLATING || tape->sensealg > B200_SENSE_GAUSS)
     return set_err(ctx, B200_ERR_ARG, "tape recorded with sensealg %d", tape->sensealg);
-  const int flavor = tape->sensealg == B200_SENSE_INTERPOLATING ? FL_ADJ_NODE_INTERP : FL_ADJ_NODE_BACKSOLVE;
+  const int flavor = tape->sensealg == B200_SENSE_BACKSOLVE ? FL_ADJ_NODE_BACKSOLVE : FL_ADJ_NODE_INTERP;
   std::vector<void*> temps;
   const float* dL_d;
   if ((rc = to_device(ctx, dL_du, (size_t)tape->n_out * tape->vec_elems, o->ptr_kind, &dL_d, temps))) return rc;
@@ -1237,7 +1240,7 @@ extern "C" int b200_mshoot_adjoint(b200_ctx* ctx, const b200_model* model, b200_
   // one group's adjoint on the context that owns its tape; its parameter gradient is added to dp_acc
   auto adj_group = [&](b200_ctx* c, int g, float* dp_acc, std::vector<void*>& tmp) -> int {
     b200_tape* t = tapes[g];
-    const int flavor = t->sensealg == B200_SENSE_INTERPOLATING ? FL_ADJ_NODE_INTERP : FL_ADJ_NODE_BACKSOLVE;
+    const int flavor = t->sensealg == B200_SENSE_BACKSOLVE ? FL_ADJ_NODE_BACKSOLVE : FL_ADJ_NODE_INTERP;
     float *lam = nullptr, *mu = nullptr;
     int r = adjoint_core(c, t, flavor, dL_d + row0[g] * B * D, o, &lam, &mu, stats ? stats + g : nullptr);
     if (r < 0) return r;
@@ -1323,7 +1326,7 @@ extern "C" int b200_node_train_step(b200_ctx* ctx, const b200_model* model, floa
   if (!p || !adam_m || !adam_v || !u0 || !data) return set_err(ctx, B200_ERR_ARG, "null p/adam state/u0/data");
   if (step < 1 || !(lr > 0.f)) return set_err(ctx, B200_ERR_ARG, "step must be >= 1 and lr > 0");
   if (d_in < 1 || augment < 0 || d_in + augment != m.dims[0]) return set_err(ctx, B200_ERR_ARG, "state size mismatch");
-  if (o->sensealg != B200_SENSE_INTERPOLATING && o->sensealg != B200_SENSE_BACKSOLVE) return set_err(ctx, B200_ERR_ARG, "sensealg");
+  if (o->sensealg < B200_SENSE_INTERPOLATING || o->sensealg > B200_SENSE_GAUSS) return set_err(ctx, B200_ERR_ARG, "sensealg");
   if (o->save_everystep) return set_err(ctx, B200_ERR_UNSUPPORTED, "train step needs saveat / the end state (save_everystep = 0)");
   const int n_out = (o->save_start ? 1 : 0) + nsave + (o->save_end ? 1 : 0);
   if (n_out < 1) return set_err(ctx, B200_ERR_ARG, "no saved point to compare with the data");
@@ -1362,7 +1365,7 @@ extern "C" int b200_node_train_step(b200_ctx* ctx, const b200_model* model, floa
   temps.push_back(dL); temps.push_back(loss_d); temps.push_back(partial);
   sse_loss_kernel<<<nblk, 256, 0, ctx->stream>>>(t->out_u, data_d, (long long)nsaved, dL, partial);
   sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(partial, nblk, loss_d);
-  const int flavor = o->sensealg == B200_SENSE_INTERPOLATING ? FL_ADJ_NODE_INTERP : FL_ADJ_NODE_BACKSOLVE;
+  const int flavor = o->sensealg == B200_SENSE_BACKSOLVE ? FL_ADJ_NODE_BACKSOLVE : FL_ADJ_NODE_INTERP;
   float *lam = nullptr, *mu = nullptr;
   rc = adjoint_core(ctx, t, flavor, dL, o, &lam, &mu, adj_stats);
   if (rc == 0) {

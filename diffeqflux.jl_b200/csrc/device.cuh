@@ -186,6 +186,7 @@ struct SolveParams {
   float* slabs;          // [nctas][4][ppad]
   float* mu;             // [2][ppad]
   float* mu_out;         // [ppad]
+  int mu_in_norm;        // 1: mu is a state of the adjoint ODE (Interpolating / Backsolve); 0: quadrature (Quadrature / Gauss adjoints)
   // FFJORD
   unsigned long long seed;
   int noise_per_call;

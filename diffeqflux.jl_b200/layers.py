@@ -153,6 +153,26 @@ class BacksolveAdjoint:
     code: int = N.SENSE_BACKSOLVE
 
 
+@dataclass
+class QuadratureAdjoint:
+    """`QuadratureAdjoint(; abstol = 1e-6, reltol = 1e-3)` (re-exported at src/DiffEqFlux.jl:19-20): lambda alone is
+    integrated backwards against the dense forward output; dp = int lambda^T df/dp dt is a quadrature.  On the B200 path
+    the quadrature uses the Runge-Kutta weights of the lambda solve's own stages (error O(solver tolerance)); `abstol` /
+    `reltol` of the reference's adaptive Gauss-Kronrod rule are accepted and ignored."""
+    abstol: float = 1e-6
+    reltol: float = 1e-3
+    autojacvec: object = None
+    code: int = N.SENSE_QUADRATURE
+
+
+@dataclass
+class GaussAdjoint:
+    """`GaussAdjoint()` (src/DiffEqFlux.jl:19-20): same engine as QuadratureAdjoint on the B200 path."""
+    autojacvec: object = None
+    checkpointing: bool = False
+    code: int = N.SENSE_GAUSS
+
+
 class ZygoteVJP:
     pass
 
@@ -327,8 +347,8 @@ class _Solve:
         sa = self.kw.get("sensealg", InterpolatingAdjoint(autojacvec=ZygoteVJP()))   # src/neural_de.jl:57
         if isinstance(sa, type):
             sa = sa()
-        if not isinstance(sa, (InterpolatingAdjoint, BacksolveAdjoint)):
-            raise UnsupportedError(f"sensealg {type(sa).__name__}: supported are InterpolatingAdjoint, BacksolveAdjoint")
+        if not isinstance(sa, (InterpolatingAdjoint, BacksolveAdjoint, QuadratureAdjoint, GaussAdjoint)):
+            raise UnsupportedError(f"sensealg {type(sa).__name__}: supported are Interpolating, Backsolve, Quadrature and Gauss adjoints")
         self.sense = sa.code
 
     def opts(self, on_device, want_tape):

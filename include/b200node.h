@@ -55,6 +55,11 @@ extern "C" {
 #define B200_SENSE_NONE (-1)          /* forward only, keep no tape */
 #define B200_SENSE_INTERPOLATING 0    /* InterpolatingAdjoint: dense forward output kept in HBM */
 #define B200_SENSE_BACKSOLVE 1        /* BacksolveAdjoint(checkpointing=true): saved states only */
+#define B200_SENSE_QUADRATURE 2       /* QuadratureAdjoint (src/DiffEqFlux.jl:19-20): lambda is integrated alone against the dense
+                                         forward output; dp = int lambda^T df/dp dt is a quadrature, not an ODE state (it has no
+                                         part in the step control).  The quadrature uses the Runge-Kutta weights of the lambda
+                                         solve's own stages (5th order) instead of the reference's adaptive Gauss-Kronrod rule */
+#define B200_SENSE_GAUSS 3            /* GaussAdjoint (src/DiffEqFlux.jl:19-20): same engine as B200_SENSE_QUADRATURE */
 
 #define B200_PTR_HOST 0
 #define B200_PTR_DEVICE 1

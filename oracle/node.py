@@ -23,7 +23,7 @@ from .mlp import MLP
 from .philox import normal
 
 f32 = np.float32
-SENSE_INTERPOLATING, SENSE_BACKSOLVE = 0, 1
+SENSE_INTERPOLATING, SENSE_BACKSOLVE, SENSE_QUADRATURE, SENSE_GAUSS = 0, 1, 2, 3
 
 
 # ----------------------------------------------------------------------------- problems
@@ -154,9 +154,15 @@ class Adjoint:
 
 
 def adjoint(problem, p, fwd: Forward, dL_du, *, sensealg=SENSE_INTERPOLATING, abstol=1e-6,
-            reltol=1e-3, maxiters=100000, record_trace=False, augment=0, dt0=None) -> Adjoint:
+            reltol=1e-3, maxiters=100000, record_trace=False, augment=0, dt0=None, quad_abstol=1e-6,
+            quad_reltol=1e-3) -> Adjoint:
     """Backward solve from t1 to t0 of d(lambda)/dt = -(df/dy)^T lambda, d(mu)/dt = -(df/dp)^T lambda
-    (and dy/dt = f for Backsolve) with lambda += dL/du(t_i) at every saved time t_i."""
+    (and dy/dt = f for Backsolve) with lambda += dL/du(t_i) at every saved time t_i.
+    sensealg = SENSE_QUADRATURE / SENSE_GAUSS: see quadrature_adjoint."""
+    if sensealg in (SENSE_QUADRATURE, SENSE_GAUSS):
+        return quadrature_adjoint(problem, p, fwd, dL_du, abstol=abstol, reltol=reltol, maxiters=maxiters,
+                                  record_trace=record_trace, augment=augment, dt0=dt0, quad_abstol=quad_abstol,
+                                  quad_reltol=quad_reltol)
     ts = fwd.ts
     dL = np.asarray(dL_du, dtype=np.float32)
     assert dL.shape == fwd.us.shape, (dL.shape, fwd.us.shape)
@@ -206,6 +212,107 @@ def adjoint(problem, p, fwd: Forward, dL_du, *, sensealg=SENSE_INTERPOLATING, ab
     if augment:
         lam = lam[:, :NS - augment]
     return Adjoint(du0=lam, dp=mu, stats=sol.stats)
+
+
+# ----------------------------------------------------------------------------- QuadratureAdjoint
+# Gauss-Kronrod (7, 15) rule on [-1, 1] (QuadGK.jl default order 7): Kronrod nodes x >= 0, Kronrod weights, Gauss weights
+_GK_X = np.array([0.991455371120812639206854697526329, 0.949107912342758524526189684047851, 0.864864423359769072789712788640926,
+                  0.741531185599394439863864773280788, 0.586087235467691130294144838258730, 0.405845151377397166906606412076961,
+                  0.207784955007898467600689403773245, 0.0])
+_GK_WK = np.array([0.022935322010529224963732008058970, 0.063092092629978553290700663189204, 0.104790010322250183839876322541518,
+                   0.140653259715525918745189590510238, 0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+                   0.204432940075298892414161999234649, 0.209482141084727828012999174891714])
+_GK_WG = np.array([0.129484966168869693270611432679082, 0.279705391489276667901467771423780, 0.381830050505118944950369775488975,
+                   0.417959183673469387755102040816327])     # Gauss-Legendre 7 weights for nodes _GK_X[1], [3], [5], [7]
+
+
+def quadgk_vec(f, a, b, atol, rtol, maxevals=10**5):
+    """QuadGK.jl `quadgk(f, a, b; atol, rtol)` for a vector-valued integrand [UPSTREAM-RECALL; QuadGK is a dependency of
+    SciMLSensitivity, not vendored]: 15-point Kronrod estimate I, error E = ||I - G7|| (Euclidean norm), the segment with
+    the largest error is bisected until sum(E) <= max(atol, rtol * ||sum(I)||).  float64 throughout."""
+    def rule(lo, hi):
+        c, h = 0.5 * (lo + hi), 0.5 * (hi - lo)
+        f0 = f(c)
+        ik, ig = _GK_WK[7] * f0, _GK_WG[3] * f0
+        for j in range(7):
+            fs = f(c - h * _GK_X[j]) + f(c + h * _GK_X[j])
+            ik = ik + _GK_WK[j] * fs
+            if j % 2 == 1:
+                ig = ig + _GK_WG[j // 2] * fs
+        return ik * h, float(np.linalg.norm((ik - ig) * h))
+    segs = [(a, b) + rule(a, b)]
+    nev = 15
+    while True:
+        tot = sum(sg[2] for sg in segs)
+        err = sum(sg[3] for sg in segs)
+        if err <= max(atol, rtol * float(np.linalg.norm(tot))) or nev >= maxevals:
+            return tot, err
+        k = max(range(len(segs)), key=lambda i: segs[i][3])
+        lo, hi, _, _ = segs.pop(k)
+        mid = 0.5 * (lo + hi)
+        segs.append((lo, mid) + rule(lo, mid))
+        segs.append((mid, hi) + rule(mid, hi))
+        nev += 30
+
+
+def quadrature_adjoint(problem, p, fwd: Forward, dL_du, *, abstol=1e-6, reltol=1e-3, maxiters=100000, record_trace=False,
+                       augment=0, dt0=None, quad_abstol=1e-6, quad_reltol=1e-3) -> Adjoint:
+    """SciMLSensitivity `QuadratureAdjoint(abstol = 1e-6, reltol = 1e-3)` (re-exported at /root/reference/src/DiffEqFlux.jl:19-20;
+    used at /root/reference/test/AdvancedNeuralDE/second_order_ode_tests.jl:59,83), restated [UPSTREAM-RECALL]:
+      1. lambda ALONE is integrated from t1 to t0 with the same Tsit5 loop (error norm over lambda only, the solve's
+         abstol / reltol), y(t) from the forward dense output, lambda += dL/du(t_i) at every saved time, dense output kept;
+      2. dp = sum over the intervals between saved times of quadgk(t -> lambda(t)^T df/dp(y(t), p), t_i, t_{i+1};
+         atol = sensealg.abstol, rtol = sensealg.reltol);  du0 = lambda(t0).
+    GaussAdjoint is treated alike (its Gauss-Legendre callbacks integrate the same integrand)."""
+    assert fwd.sol.dense, "QuadratureAdjoint needs the forward dense output"
+    ts = fwd.ts
+    dL = np.asarray(dL_du, dtype=np.float32)
+    t0, t1 = fwd.t0, fwd.t1
+    B, NS = fwd.us.shape[1:]
+    counter = [0]
+    jumps = {float(t): i for i, t in enumerate(ts)}
+    interior = [t for t in ts[::-1] if min(t0, t1) < t < max(t0, t1)]
+
+    def rhs(state, t):
+        y = tsit5.dense_eval(fwd.sol.dense, t)
+        _, ybar, _ = problem.vjp(p, y, state[0], counter[0], 1)
+        counter[0] += 1
+        return [-ybar]
+
+    def jump(state, t):
+        i = jumps.get(float(t))
+        return None if i is None else [(state[0] + dL[i]).astype(np.float32)]
+
+    def init_jump(state):
+        mod = jump(state, t1)
+        return state if mod is None else mod
+
+    sol = tsit5.solve(rhs, [np.zeros((B, NS), np.float32)], t1, t0, abstol=abstol, reltol=reltol, saveat=(), save_start=False,
+                      save_end=True, save_everystep=False, tstops=interior, on_tstop=jump, init_jump=init_jump,
+                      maxiters=maxiters, record_trace=record_trace, dt0=dt0, dense=True)
+    lam_dense = sol.dense                       # steps run from t1 down to t0; the jumps sit on step boundaries
+
+    def lam_at(t, lower_side):
+        """lambda(t) from the adjoint's dense output; at a jump time the value depends on the side: quadgk never
+        evaluates the end points, so only interior times occur and the bracketing step is unambiguous."""
+        return tsit5.dense_eval(lam_dense, f32(t))
+
+    def integrand(t):
+        y = tsit5.dense_eval(fwd.sol.dense, f32(t))
+        lam = lam_at(t, False)
+        _, _, pbar = problem.vjp(p, y, lam, 0, 1)
+        return pbar.astype(np.float64)
+
+    knots = sorted(set([float(t0), float(t1)] + [float(t) for t in ts if min(t0, t1) < t < max(t0, t1)]))
+    dp = np.zeros(p.size, np.float64)
+    for a, b in zip(knots[:-1], knots[1:]):
+        val, _ = quadgk_vec(integrand, a, b, quad_abstol, quad_reltol)
+        dp += val
+    # d(mu)/dt = -lambda^T df/dp integrated from t1 DOWN to t0: mu(t0) = + int_{t0}^{t1} lambda^T df/dp dt
+    lam = sol.u_final[0]
+    if augment:
+        lam = lam[:, :NS - augment]
+    return Adjoint(du0=lam, dp=dp.astype(np.float32), stats=sol.stats)
 
 
 # ----------------------------------------------------------------------------- FFJORD wrapper

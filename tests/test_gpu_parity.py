@@ -563,3 +563,34 @@ def test_dimmover_and_ffjord_sampling():
     close(back, xs, rtol=1e-4, what="flow^-1(flow(x))")
     d = dfx.FFJORDDistribution(ff, p, st)
     assert len(d) == 2 and d.rand(64, np.random.default_rng(1)).shape == (64, 2) and d.logpdf(xs).shape == (512,)
+
+
+@pytest.mark.parametrize("sa", ["quadrature", "gauss"])
+def test_quadrature_adjoint(sa):
+    """N1: QuadratureAdjoint / GaussAdjoint (src/DiffEqFlux.jl:19-20; test/AdvancedNeuralDE/second_order_ode_tests.jl:59,83).
+    The oracle restates the reference: lambda alone integrated against the dense forward output, dp by adaptive
+    Gauss-Kronrod (QuadGK 7/15) between the saved times.  The CUDA path integrates lambda alone as well (mu is not in the
+    error norm: fewer steps than InterpolatingAdjoint on the same problem) and forms dp with the Runge-Kutta weights of
+    those steps: du0 and dp element-wise within rtol 1e-4."""
+    rng, mlp, p, chain = make([16, 64, 16], 3, scale=3.0)
+    u0 = rng.standard_normal((64, 16)).astype(np.float32)
+    kw = dict(abstol=1e-6, reltol=1e-6, saveat=[0.3, 0.7, 1.0])
+    prob = onode.NodeProblem(mlp)
+    fw = onode.forward(prob, p, u0, 0.0, 1.0, dense=True, **kw)
+    dL = np.sin(fw.us).astype(np.float32)
+    adj = onode.adjoint(prob, p, fw, dL, sensealg=onode.SENSE_QUADRATURE, abstol=1e-6, reltol=1e-6, quad_abstol=1e-8, quad_reltol=1e-6)
+    ref_i = onode.adjoint(prob, p, fw, dL, sensealg=onode.SENSE_INTERPOLATING, abstol=1e-6, reltol=1e-6)
+    sens = dfx.QuadratureAdjoint(abstol=1e-8, reltol=1e-6) if sa == "quadrature" else dfx.GaussAdjoint()
+    node = dfx.NeuralODE(chain, (0.0, 1.0), dfx.Tsit5(), sensealg=sens, **kw)
+    sol, back = node.pullback(u0, p)
+    du0, dp = back(dL)
+    check_steps(sol.stats, fw.stats, "forward", True)
+    ast = node.last["adjoint_stats"]
+    # lambda's own step sequence: within one step of the oracle's (two interior tstops: whether the step before a stop
+    # lands a few 1e-4 short of it decides about one extra remainder step, DESIGN.md section 2), no rejections
+    assert abs(ast.naccept - adj.stats.naccept) <= 1 and ast.nreject == adj.stats.nreject == 0, (counts(ast), counts(adj.stats))
+    assert ast.nf == 3 + 6 * ast.naccept + 2
+    assert adj.stats.naccept < ref_i.stats.naccept          # without mu's rounding noise in the norm the ramp-up is shorter
+    close(du0, adj.du0, what="du0")
+    close(dp, adj.dp, what="dp")
+    close(dp, ref_i.dp, what="dp vs InterpolatingAdjoint")

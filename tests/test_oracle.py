@@ -304,3 +304,27 @@ def test_training_step_and_dimmover_restatement():
         loss, p, m, v, _ = otrain.train_step(prob, p, u0, data, 0.0, 1.0, it, m, v, saveat=ts, lr=0.05)
         losses.append(loss)
     assert losses[-1] < losses[0]
+
+
+def test_quadrature_adjoint_agrees_with_interpolating():
+    """The QuadratureAdjoint restatement (lambda-only dense solve + adaptive Gauss-Kronrod) and the InterpolatingAdjoint
+    restatement (mu inside the ODE state) compute the same gradient; the 7/15 rule integrates a degree-20 polynomial
+    exactly and the adaptive driver reaches the requested tolerance on a peaked integrand."""
+    val, err = node.quadgk_vec(lambda t: np.array([t ** 20, 1.0]), 0.0, 2.0, 0.0, 1e-13)
+    np.testing.assert_allclose(val, [2.0 ** 21 / 21, 2.0], rtol=1e-12)
+    val, err = node.quadgk_vec(lambda t: np.array([1.0 / (1e-3 + (t - 0.3) ** 2)]), 0.0, 1.0, 1e-10, 1e-10)
+    exact = (np.arctan(0.7 / np.sqrt(1e-3)) + np.arctan(0.3 / np.sqrt(1e-3))) / np.sqrt(1e-3)
+    assert abs(val[0] - exact) <= 1e-8 * exact
+    rng = np.random.default_rng(3)
+    mlp = MLP([8, 32, 8], [ACT_TANH, ACT_ID])
+    p = mlp.init(rng, scale=2.5)
+    u0 = rng.standard_normal((16, 8)).astype(np.float32)
+    prob = node.NodeProblem(mlp)
+    kw = dict(abstol=1e-6, reltol=1e-6)
+    fw = node.forward(prob, p, u0, 0.0, 1.0, saveat=[0.4, 1.0], dense=True, **kw)
+    dL = np.cos(fw.us).astype(np.float32)
+    ai = node.adjoint(prob, p, fw, dL, sensealg=node.SENSE_INTERPOLATING, **kw)
+    aq = node.adjoint(prob, p, fw, dL, sensealg=node.SENSE_QUADRATURE, quad_abstol=1e-8, quad_reltol=1e-6, **kw)
+    assert np.abs(aq.dp - ai.dp).max() <= 2e-5 * np.abs(ai.dp).max()
+    assert np.abs(aq.du0 - ai.du0).max() <= 2e-5 * np.abs(ai.du0).max()
+    assert aq.stats.nf == 3 + 6 * (aq.stats.naccept + aq.stats.nreject) + 1      # one FSAL re-evaluation at the interior jump
