@@ -21,7 +21,8 @@ constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAX_CTAS = 1024;
 constexpr int MAX_RANKS = 8;
-constexpr int NSLAB = 7;   // per-CTA weight-gradient slabs: stages 2..6 (0..4) + the two FSAL slabs G1/G7 (5, 6; swapped on accept)
+constexpr int NSTEP_SLAB = 7;  // per-CTA weight-gradient slabs of a step: stages 2..6 (0..4) + the two FSAL slabs G1/G7 (5, 6; swapped on accept)
+constexpr int NSLAB = 8;       // + slab 7: the CTA's running quadrature sum of the Quadrature / Gauss adjoints
 
 enum Flavor : int {
   FL_FWD_NODE = 0,
@@ -1393,15 +1394,15 @@ struct Solver {
     using namespace b200tc;
     const int pp = P.mlp.ppad;
     float* stage = reinterpret_cast<float*>(tc_base());
-    constexpr int BUF = MU_CB * NSLAB * MU_SUB;       // floats per staging buffer
+    constexpr int BUF = MU_CB * NSTEP_SLAB * MU_SUB;  // floats per staging buffer
     const int nb = (P.nctas + MU_CB - 1) / MU_CB;
     auto issue = [&](int b) {                         // all threads: one copy each (a single issuing thread spent
       const int buf = b & 1, c0 = b * MU_CB, cn = min(MU_CB, P.nctas - c0);   // ~1/3 of the phase issuing 21 copies per batch)
       uint64_t* bar = reinterpret_cast<uint64_t*>(&ss.mu_full[buf]);
-      if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(cn * NSLAB * n * 4));
-      if (tid < cn * NSLAB) {
-        const int c = tid / NSLAB, sl = tid - c * NSLAB;
-        bulk_g2s(stage + buf * BUF + (c * NSLAB + sl) * MU_SUB, P.slabs + ((long long)(c0 + c) * NSLAB + sl) * pp + slo,
+      if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(cn * NSTEP_SLAB * n * 4));
+      if (tid < cn * NSTEP_SLAB) {
+        const int c = tid / NSTEP_SLAB, sl = tid - c * NSTEP_SLAB;
+        bulk_g2s(stage + buf * BUF + (c * NSTEP_SLAB + sl) * MU_SUB, P.slabs + ((long long)(c0 + c) * NSLAB + sl) * pp + slo,
                  (uint32_t)(n * 4), bar);
       }
     };
@@ -1419,7 +1420,7 @@ struct Solver {
         for (int k = 0; k < MU_SUB / NTHREADS; ++k) {
           const int jj = tid + k * NTHREADS;
           if (jj < n) {
-            const float* q = sb + c * NSLAB * MU_SUB + jj;
+            const float* q = sb + c * NSTEP_SLAB * MU_SUB + jj;
             const float k1 = q[g1 * MU_SUB], k7 = q[g7 * MU_SUB];
             float a = c_tab.a[6][0] * k1, e = c_tab.bt[0] * k1;
 #pragma unroll
@@ -1436,6 +1437,42 @@ struct Solver {
       }
       sync();                                         // buffer drained by every thread
       if (b + 2 < nb) issue(b + 2);
+    }
+  }
+  // Quadrature / Gauss adjoints: mu is not a state of the adjoint ODE, so no batch-wide total is needed per step.  After
+  // an ACCEPTED step every CTA adds dt * sum_s b_s G_s of its own slabs to its running slab 7 (local traffic only: no grid
+  // barrier, no cross-CTA or cross-rank exchange); the CTAs' sums meet once, after the last step (solver.cuh epilogue).
+  __device__ void quad_accumulate(float dt, int g1) {
+    const int pp = P.mlp.ppad;
+    float* base = P.slabs + (long long)cta * NSLAB * pp;
+    constexpr int U = 4;                                   // float4 groups per thread per pass: 28 loads in flight
+    for (int j0 = tid * 4; j0 < pp; j0 += NTHREADS * 4 * U) {
+      float4 k1[U], ks[U][5], acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * NTHREADS * 4;
+        if (j < pp) {
+          k1[u] = __ldcg(reinterpret_cast<const float4*>(base + (long long)g1 * pp + j));
+#pragma unroll
+          for (int s5 = 0; s5 < 5; ++s5) ks[u][s5] = __ldcg(reinterpret_cast<const float4*>(base + (long long)s5 * pp + j));
+          acc[u] = __ldcg(reinterpret_cast<const float4*>(base + 7ll * pp + j));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * NTHREADS * 4;
+        if (j < pp) {
+          float4 a = make_float4(c_tab.a[6][0] * k1[u].x, c_tab.a[6][0] * k1[u].y, c_tab.a[6][0] * k1[u].z, c_tab.a[6][0] * k1[u].w);
+#pragma unroll
+          for (int s5 = 0; s5 < 5; ++s5) {
+            a.x = fmaf(c_tab.a[6][1 + s5], ks[u][s5].x, a.x); a.y = fmaf(c_tab.a[6][1 + s5], ks[u][s5].y, a.y);
+            a.z = fmaf(c_tab.a[6][1 + s5], ks[u][s5].z, a.z); a.w = fmaf(c_tab.a[6][1 + s5], ks[u][s5].w, a.w);
+          }
+          float4 v = acc[u];
+          v.x = fmaf(dt, a.x, v.x); v.y = fmaf(dt, a.y, v.y); v.z = fmaf(dt, a.z, v.z); v.w = fmaf(dt, a.w, v.w);
+          __stcg(reinterpret_cast<float4*>(base + 7ll * pp + j), v);
+        }
+      }
     }
   }
   // every CTA advances the mu-exchange epoch together (call after mu_reduce, CTA-uniformly)

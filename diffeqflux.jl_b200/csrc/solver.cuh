@@ -322,7 +322,7 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
 #ifdef B200_TC_PROF
     qf[1] += clock64() - q_t0; q_t0 = clock64();
 #endif
-    if constexpr (T::adj) {
+    if constexpr (T::adj) if (P.mu_in_norm) {
       S.barrier_reduce(0.0, 0.0, false);   // every CTA's slabs of this step complete (local ordering only)
 #ifdef B200_TC_PROF
       qf[2] += clock64() - q_t0; q_t0 = clock64();
@@ -333,7 +333,6 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
         const float m0 = mu[j];
         const float m1 = fmaf(dt, totA, m0);
         mun[j] = m1;
-        if (!P.mu_in_norm) return 0.f;          // quadrature adjoints: mu = sum_steps dt sum_s b_s G_s, no part in the step control
         const float ut = dt * totE;
         const float sk = fmaf(fmaxf(fabsf(m0), fabsf(m1)), P.reltol, P.abstol);
         const float x = ut / sk;
@@ -395,6 +394,7 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
 
     // ---- accepted step
     const float tnew = ss.tnew;
+    if constexpr (T::adj) if (!P.mu_in_norm) S.quad_accumulate(dt, g1);   // (its slab reads are ordered by the S.sync() above)
     if constexpr (!T::adj) {
       // saveat: 4th-order interpolant with the integrator's dt (OrdinaryDiffEq savevalues!)
       int si = ss.si, oi = ss.out_idx;
@@ -475,6 +475,15 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
 
   // ------------------------------------------------------------------ epilogue
   S.sync();
+  if constexpr (T::adj) {
+    if (!P.mu_in_norm && !S.aborted()) {
+      // quadrature adjoints: the one and only cross-CTA (and cross-rank) reduction of the parameter gradient
+      S.barrier_reduce(0.0, 0.0, false);
+      float* mo = P.mu_out;
+      S.mu_reduce(7, 1.f, -1, 0.f, -1, [&](int j, float tot, float) { mo[j] = tot; return 0.f; });
+      S.mu_reduce_done();
+    }
+  }
   if (P.world > 1 && !S.aborted()) {
     // closing exchange: once it completes every rank has consumed all earlier mailbox slots, so the
     // next solve may overwrite them
@@ -498,12 +507,14 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
       }
     });
     if constexpr (T::adj) {
-      const float* mu = P.mu + (long long)ss.mu_cur * M.ppad;
-      const int pp = M.ppad;
-      int chunk = (pp + P.nctas - 1) / P.nctas;
-      chunk = (chunk + 3) & ~3;
-      const int lo = cta * chunk, hi = min(pp, lo + chunk);
-      for (int j = lo + tid; j < hi; j += NTHREADS) P.mu_out[j] = mu[j];
+      if (P.mu_in_norm) {
+        const float* mu = P.mu + (long long)ss.mu_cur * M.ppad;
+        const int pp = M.ppad;
+        int chunk = (pp + P.nctas - 1) / P.nctas;
+        chunk = (chunk + 3) & ~3;
+        const int lo = cta * chunk, hi = min(pp, lo + chunk);
+        for (int j = lo + tid; j < hi; j += NTHREADS) P.mu_out[j] = mu[j];
+      }
     }
     if (cta == 0 && tid == 0) {
       int n_out = ss.out_idx;

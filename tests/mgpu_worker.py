@@ -29,7 +29,7 @@ def main():
     B = 512
     u0 = rng.standard_normal((B, dims[0])).astype(np.float32)
     dL = np.cos(np.arange(B * dims[0], dtype=np.float32).reshape(1, B, dims[0]) * 0.01)
-    sa = dfx.BacksolveAdjoint() if sense else dfx.InterpolatingAdjoint()
+    sa = {0: dfx.InterpolatingAdjoint(), 1: dfx.BacksolveAdjoint(), 2: dfx.QuadratureAdjoint()}[sense]
     kw = dict(abstol=1e-4, reltol=1e-4, save_everystep=False, save_start=False, sensealg=sa)
     kw.update(dict(path=2) if tc else dict(tile=32))
     node = dfx.NeuralODE(chain, (0.0, 1.0), dfx.Tsit5(), **kw)

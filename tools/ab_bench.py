@@ -22,7 +22,7 @@ def main():
     p_d, u0_d = torch.from_numpy(p).to(dev), torch.from_numpy(u0).to(dev)
     dL = torch.ones((1, B, 64), device=dev)
     chain = dfx.Chain(dfx.Dense(64, 256, dfx.tanh), dfx.Dense(256, 256, dfx.tanh), dfx.Dense(256, 64))
-    sa = dfx.BacksolveAdjoint() if sense == "backsolve" else dfx.InterpolatingAdjoint()
+    sa = {"backsolve": dfx.BacksolveAdjoint(), "interp": dfx.InterpolatingAdjoint(), "quad": dfx.QuadratureAdjoint()}[sense]
     node = dfx.NeuralODE(chain, bench.TSPAN, dfx.Tsit5(), abstol=bench.TOL, reltol=bench.TOL, save_everystep=False,
                          save_start=False, sensealg=sa, max_dense_steps=64)
     tf, ta = [], []
