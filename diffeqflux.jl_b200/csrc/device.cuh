@@ -1442,37 +1442,36 @@ struct Solver {
   // Quadrature / Gauss adjoints: mu is not a state of the adjoint ODE, so no batch-wide total is needed per step.  After
   // an ACCEPTED step every CTA adds dt * sum_s b_s G_s of its own slabs to its running slab 7 (local traffic only: no grid
   // barrier, no cross-CTA or cross-rank exchange); the CTAs' sums meet once, after the last step (solver.cuh epilogue).
+  // (kept small on purpose -- one float4 group per pass, the passes two ahead pulled towards L2 by prefetches: a wider,
+  // register-hungry version drove the register allocation of the whole FP32-FFMA adjoint kernels from 192 to 255)
   __device__ void quad_accumulate(float dt, int g1) {
     const int pp = P.mlp.ppad;
     float* base = P.slabs + (long long)cta * NSLAB * pp;
-    constexpr int U = 4;                                   // float4 groups per thread per pass: 28 loads in flight
-    for (int j0 = tid * 4; j0 < pp; j0 += NTHREADS * 4 * U) {
-      float4 k1[U], ks[U][5], acc[U];
+    const int stride = NTHREADS * 4;
+    auto prefetch = [&](int j) {
+      if (j < pp) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long long)g1 * pp + j));
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * NTHREADS * 4;
-        if (j < pp) {
-          k1[u] = __ldcg(reinterpret_cast<const float4*>(base + (long long)g1 * pp + j));
-#pragma unroll
-          for (int s5 = 0; s5 < 5; ++s5) ks[u][s5] = __ldcg(reinterpret_cast<const float4*>(base + (long long)s5 * pp + j));
-          acc[u] = __ldcg(reinterpret_cast<const float4*>(base + 7ll * pp + j));
-        }
+        for (int s5 = 0; s5 < 5; ++s5) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long long)s5 * pp + j));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 7ll * pp + j));
       }
+    };
+    prefetch(tid * 4);
+    prefetch(tid * 4 + stride);
+    for (int j = tid * 4; j < pp; j += stride) {
+      prefetch(j + 2 * stride);
+      const float4 k1 = __ldcg(reinterpret_cast<const float4*>(base + (long long)g1 * pp + j));
+      float4 a = make_float4(c_tab.a[6][0] * k1.x, c_tab.a[6][0] * k1.y, c_tab.a[6][0] * k1.z, c_tab.a[6][0] * k1.w);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * NTHREADS * 4;
-        if (j < pp) {
-          float4 a = make_float4(c_tab.a[6][0] * k1[u].x, c_tab.a[6][0] * k1[u].y, c_tab.a[6][0] * k1[u].z, c_tab.a[6][0] * k1[u].w);
-#pragma unroll
-          for (int s5 = 0; s5 < 5; ++s5) {
-            a.x = fmaf(c_tab.a[6][1 + s5], ks[u][s5].x, a.x); a.y = fmaf(c_tab.a[6][1 + s5], ks[u][s5].y, a.y);
-            a.z = fmaf(c_tab.a[6][1 + s5], ks[u][s5].z, a.z); a.w = fmaf(c_tab.a[6][1 + s5], ks[u][s5].w, a.w);
-          }
-          float4 v = acc[u];
-          v.x = fmaf(dt, a.x, v.x); v.y = fmaf(dt, a.y, v.y); v.z = fmaf(dt, a.z, v.z); v.w = fmaf(dt, a.w, v.w);
-          __stcg(reinterpret_cast<float4*>(base + 7ll * pp + j), v);
-        }
+      for (int s5 = 0; s5 < 5; ++s5) {
+        const float4 ks = __ldcg(reinterpret_cast<const float4*>(base + (long long)s5 * pp + j));
+        a.x = fmaf(c_tab.a[6][1 + s5], ks.x, a.x); a.y = fmaf(c_tab.a[6][1 + s5], ks.y, a.y);
+        a.z = fmaf(c_tab.a[6][1 + s5], ks.z, a.z); a.w = fmaf(c_tab.a[6][1 + s5], ks.w, a.w);
       }
+      float4* q = reinterpret_cast<float4*>(base + 7ll * pp + j);
+      float4 v = __ldcg(q);
+      v.x = fmaf(dt, a.x, v.x); v.y = fmaf(dt, a.y, v.y); v.z = fmaf(dt, a.z, v.z); v.w = fmaf(dt, a.w, v.w);
+      __stcg(q, v);
     }
   }
   // every CTA advances the mu-exchange epoch together (call after mu_reduce, CTA-uniformly)

@@ -594,3 +594,25 @@ def test_quadrature_adjoint(sa):
     close(du0, adj.du0, what="du0")
     close(dp, adj.dp, what="dp")
     close(dp, ref_i.dp, what="dp vs InterpolatingAdjoint")
+
+
+def test_cfg5_shape_augmented_192_512_512_192():
+    """BASELINE.json configs[4] at its own widths (state 128 + 64 zero-augment rows, MLP 192 -> 512 -> 512 -> 192; FP32-FFMA
+    engine: the widths exceed the tcgen05 engine's 256) on a small batch: forward counts exact, states and gradients
+    element-wise within 3 x reltol at the docs' tolerance 1e-3 (docs/src/examples/augmented_neural_ode.md:47-50) and
+    within 1e-4 at 1e-6."""
+    rng, mlp, p, chain = make([192, 512, 512, 192], 5, scale=1.0)
+    u0 = rng.standard_normal((96, 128)).astype(np.float32)
+    prob = onode.NodeProblem(mlp)
+    for tol, rtol in ((1e-3, 3e-3), (1e-6, 1e-4)):
+        kw = dict(abstol=tol, reltol=tol, save_everystep=False, save_start=False)
+        fw = onode.forward(prob, p, u0, 0.0, 1.0, dense=True, augment=64, **kw)
+        adj = onode.adjoint(prob, p, fw, np.ones_like(fw.us), sensealg=0, augment=64, abstol=tol, reltol=tol)
+        layer = dfx.AugmentedNDELayer(dfx.NeuralODE(chain, (0.0, 1.0), dfx.Tsit5(), **kw), 64)
+        sol, back = layer.pullback(u0, p)
+        du0, dp = back(np.ones_like(sol.array()))
+        assert sol.stats.engine == 0 and sol.array().shape == (1, 96, 192) and du0.shape == (96, 128)
+        check_steps(sol.stats, fw.stats, f"forward tol {tol}", True)
+        close(sol.array(), fw.us, rtol=rtol, what=f"states tol {tol}")
+        close(dp, adj.dp, rtol=rtol, what=f"dp tol {tol}")
+        close(du0, adj.du0, rtol=rtol, what=f"du0 tol {tol}")
