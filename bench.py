@@ -77,9 +77,9 @@ def tf32_peak():
     return pk["bf16_tflops_sustained"] / 2.0, pk["bf16_tflops"] / 2.0, f"derived: {src} bf16 / 2"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE adjoint solve-kernel launch at this workload (ncu --set full capture,
-# profiles/solve_kernels_r2_raw.csv if present, else the round-1 capture); algorithmic bytes are ~0 (the path is tensor bound)
-ADJ_DRAM_BYTES_PER_LAUNCH = 30.955821e9 + 29.046970e9
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE adjoint solve-kernel launch at this workload (ncu --set full capture of
+# this round's build, profiles/solve_kernels_r2_tc_raw.csv, second row); algorithmic bytes are ~0 (the path is tensor bound)
+ADJ_DRAM_BYTES_PER_LAUNCH = 29.438428e9 + 28.156291e9
 
 
 def golden_steps():
@@ -382,7 +382,7 @@ def run_gpu(args):
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                         "traffic": ADJ_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, adjoint solve kernel (dominant), profiles/",
+                         "traffic": ADJ_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, adjoint solve kernel (dominant), profiles/solve_kernels_r2_tc_raw.csv",
                          "peak_source": f"{tf32_src}: sustained {tf32_sus:.1f} TFLOP/s TF32 / 3 (burst {tf32_burst:.1f} / 3 = {tf32_burst / 3:.1f})",
                          "frac_of_burst_peak": achieved / (tf32_burst / 3.0),
                          "kernel_ms_per_step": k_ms / args.steps, "algorithmic_flop_per_step": flop,
