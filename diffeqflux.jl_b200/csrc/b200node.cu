@@ -547,6 +547,13 @@ static cudaError_t occupancy_any(int flavor, int smem_bytes, int* n) {
 }
 
 static int cudaFuncAttributes_ok(cudaError_t e) { return e == cudaSuccess ? 0 : 1; }
+// FFJORD forward with every layer width <= 64: the row-per-thread RHS (device.cuh: rhs_ffjord_fwd_rows)
+static bool rowthread_eligible(const MlpDesc& m, int flavor) {
+  if (flavor != FL_FWD_FFJORD || m.pre != B200_PRE_NONE || getenv("B200_NO_ROWTHREAD")) return false;
+  for (int l = 0; l <= m.nl; ++l)
+    if (m.dpad[l] > 64) return false;
+  return true;
+}
 // choose the tile (trajectories per CTA pass) and the grid
 static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int tile_opt, SolveParams& P,
                       int* smem_bytes) {
@@ -563,6 +570,14 @@ static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int ti
       return set_err(ctx, B200_ERR_UNSUPPORTED, "opts.tile=%d needs %d B of shared memory (> %d)", tile_opt,
                      plan_smem(m, flavor, tile_opt, sp), budget);
     best = tile_opt;
+  } else if (rowthread_eligible(m, flavor)) {
+    // one thread per trajectory: a tile is as many rows as the CTA has threads (fewer for small batches)
+    for (int TB = NTHREADS; TB >= 32; TB >>= 1) {
+      if (plan_smem(m, flavor, TB, sp) > budget) continue;
+      best = TB;
+      if ((B + TB - 1) / TB >= ctx->num_sms || TB == 32) break;     // keep every SM busy before growing the tile
+    }
+    if (!best) return set_err(ctx, B200_ERR_UNSUPPORTED, "row-per-thread FFJORD path: shared-memory plan does not fit");
   } else {
     for (int TB = 128; TB >= 8; TB >>= 1) {
       if (plan_smem(m, flavor, TB, sp) > budget) continue;
@@ -577,6 +592,7 @@ static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int ti
                      plan_smem(m, flavor, 8, sp), budget);
   }
   *smem_bytes = plan_smem(m, flavor, best, P.sp);
+  P.rowthread = (tile_opt <= 0 && rowthread_eligible(m, flavor)) ? 1 : 0;
   P.TB = best;
   P.ntiles = (B + best - 1) / best;
   int per_sm = 0;

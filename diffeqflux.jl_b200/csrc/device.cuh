@@ -187,6 +187,7 @@ struct SolveParams {
   float* slabs;          // [nctas][4][ppad]
   float* mu;             // [2][ppad]
   float* mu_out;         // [ppad]
+  int rowthread;         // FFJORD forward, all widths <= 64: one thread per trajectory (rhs_ffjord_fwd_rows)
   int mu_in_norm;        // 1: mu is a state of the adjoint ODE (Interpolating / Backsolve); 0: quadrature (Quadrature / Gauss adjoints)
   // FFJORD
   unsigned long long seed;
@@ -1017,6 +1018,10 @@ struct Solver {
         }
       });
     } else if constexpr (FL == FL_FWD_FFJORD) {
+      if (P.rowthread) {
+        rhs_ffjord_fwd_rows(tile, kout, call);
+        return;
+      }
       const int Lp = M.dpad[M.nl];
       float* mz = sm + P.sp.dl2_off;
       float* e = sm + P.sp.dl_off;
@@ -1066,6 +1071,101 @@ struct Solver {
     } else {  // FL_ADJ_FFJORD
       rhs_ffjord_adjoint(tile, kout, so, acc_store, call);
     }
+  }
+
+  // ---------------------------------------------------------------- FFJORD forward, one thread per trajectory
+  // Small networks (every width <= 64, e.g. the CNF examples' 2 -> 64 -> 64 -> 2): the 8 x 4 register tiles of tile_gemm
+  // leave most threads idle in the narrow first / last layers and pay a CTA barrier per layer.  Here thread t owns
+  // trajectory t of the tile: its 64 accumulators live in registers, the weight rows are warp-uniform (broadcast)
+  // 16-byte loads through L1, hidden activations go through shared memory column-major ([feature][row]: conflict free),
+  // and no barrier separates the layers.  acc[n] (+)= x * W[n .. ] for NQ quads of outputs.
+  template <int NQ>
+  __device__ __forceinline__ void row_axpy(float (&acc)[64], float x, const float* __restrict__ wrow) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wrow) + q);
+      acc[4 * q + 0] = fmaf(x, w.x, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(x, w.w, acc[4 * q + 3]);
+    }
+  }
+  // acc[0 .. 4 nq) += sum_k x_k * W[k][.]: x_k = xs[k * xstride], W row-major with ld floats per row
+  __device__ __forceinline__ void row_matvec(float (&acc)[64], const float* xs, int xstride, int K, const float* __restrict__ W,
+                                             int ld, int nq) {
+    // (two / four reduction indices per pass: the weight loads of the next index are in flight under the FMAs of this one)
+    if (nq <= 1) {
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) row_axpy<1>(acc, xs[k * xstride], W + (size_t)k * ld);
+    } else if (nq <= 4) {
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) row_axpy<4>(acc, xs[k * xstride], W + (size_t)k * ld);
+    } else if (nq <= 8) {
+#pragma unroll 2
+      for (int k = 0; k < K; ++k) row_axpy<8>(acc, xs[k * xstride], W + (size_t)k * ld);
+    } else {
+#pragma unroll 2
+      for (int k = 0; k < K; ++k) row_axpy<16>(acc, xs[k * xstride], W + (size_t)k * ld);
+    }
+  }
+  __device__ void rhs_ffjord_fwd_rows(int tile, float* kout, unsigned int call) {
+    const MlpDesc& M = P.mlp;
+    const int D = P.D, NV = P.NV, B = P.B, TB = P.TB, L = M.nl;
+    const int base_row = tile * TB;
+    const int Lp = M.dpad[L];
+    float* e = sm + P.sp.dl_off;                       // noise, [row][Lp] (fill_noise layout)
+    fill_noise(tile, 0u, call, e, Lp);
+    sync();
+    float acc[64];
+    for (int t = tid; t < TB; t += NTHREADS) {
+      // ---- forward: h_{l+1} = act(h_l W_l + b_l); hidden h_l kept column-major in the act_off[l] buffer
+      for (int l = 0; l < L; ++l) {
+        const int K = M.dims[l], Np = M.dpad[l + 1], N = M.dims[l + 1], nq = Np >> 2;
+        const float* bias = P.wp + M.b_off[l];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < nq) b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+          acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w;
+        }
+        if (l == 0) row_matvec(acc, sm + P.sp.act_off[0] + t * M.dpad[0], 1, K, P.wp + M.w_off[0], Np, nq);
+        else row_matvec(acc, sm + P.sp.act_off[l] + t, TB, K, P.wp + M.w_off[l], Np, nq);
+        const int a = M.act[l];
+        if (l < L - 1) {
+          float* H = sm + P.sp.act_off[l + 1] + t;
+#pragma unroll
+          for (int n = 0; n < 64; ++n)
+            if (n < N) H[n * TB] = act_apply(a, acc[n]);
+        } else if (base_row + t < B) {
+          float* o = kout + (long long)(base_row + t) * NV;
+#pragma unroll
+          for (int n = 0; n < 64; ++n)
+            if (n < D) o[n] = act_apply(a, acc[n]);
+        }
+      }
+      // ---- reverse: eJ = e^T dm/dz; delta_L = e, delta_l = (delta_{l+1} W_l^T) .* act'(h_l), in place in the h buffers
+      float tr = 0.f;
+      for (int l = L - 1; l >= 0; --l) {
+        const int N = M.dims[l + 1], Kp = M.dpad[l], K = M.dims[l], kq = Kp >> 2;
+#pragma unroll
+        for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+        if (l == L - 1) row_matvec(acc, e + t * Lp, 1, N, P.wtp + M.wt_off[l], Kp, kq);
+        else row_matvec(acc, sm + P.sp.act_off[l + 1] + t, TB, N, P.wtp + M.wt_off[l], Kp, kq);
+        if (l > 0) {
+          const int a = M.act[l - 1];
+          float* H = sm + P.sp.act_off[l] + t;
+#pragma unroll
+          for (int k = 0; k < 64; ++k)
+            if (k < K) H[k * TB] = acc[k] * act_d1(a, H[k * TB]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 64; ++k)
+            if (k < D) tr = fmaf(acc[k], e[t * Lp + k], tr);
+        }
+      }
+      if (base_row + t < B) kout[(long long)(base_row + t) * NV + D] = -tr;
+    }
+    sync();
   }
 
   // d/d(z,p) of  <lz, m(z)> - ll * <e, J(z) e>  through the doubled (h, hdot) network.
