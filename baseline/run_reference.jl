@@ -8,7 +8,9 @@
 #   julia --project=/path/to/env -t auto baseline/run_reference.jl /tmp/b200_inputs [nsteps]
 #
 # Output: wall time per forward+gradient, sol.stats (nf / naccept / nreject) of the forward solve, and
-# final_state.f32 / du0.f32 / dp.f32 next to the inputs (Float32, column-major (D, B) = the C ABI's [B][D]).
+# final_state.f32 / du0.f32 / dp.f32 / stats.txt next to the inputs (Float32, column-major (D, B) = the C ABI's [B][D]).
+# `python tools/compare_reference_dump.py DIR` then compares them with tests/golden/headline.npz: one command pins the
+# oracle (and with it the CUDA path's parity target) to the reference.
 using DiffEqFlux, OrdinaryDiffEq, SciMLSensitivity, Lux, ComponentArrays, Zygote, LinearAlgebra, Random
 
 dir = ARGS[1]
@@ -50,6 +52,25 @@ println("wall per forward+gradient [s]: ", times, "  (median ", sort(times)[cld(
 println("threads: julia ", Threads.nthreads(), ", BLAS ", BLAS.get_num_threads())
 println("RHS evals/s (forward count only is exact; adjoint nf is not exposed by the pullback): >= ",
         B * nf_fwd / sort(times)[cld(nsteps, 2)])
+# step statistics of the adjoint solve: SciMLSensitivity does not return the backward solution through the pullback, so the
+# same adjoint problem is solved once more explicitly (adjoint_sensitivities on the dense-free Backsolve formulation)
+adj_stats = try
+    _, _, adjsol = SciMLSensitivity.adjoint_sensitivities(
+        solve(ODEProblem{false}((u, p, t) -> first(model(u, p, st)), u0, (0.0f0, 1.0f0), ps), Tsit5(); save_everystep = false,
+              save_start = false, abstol = tol, reltol = tol), Tsit5();
+        t = [1.0f0], dgdu_discrete = (out, u, p, t, i) -> (out .= 1), sensealg = BacksolveAdjoint(; autojacvec = ZygoteVJP()),
+        abstol = tol, reltol = tol, return_adjoint_solution = true)      # keyword available in recent SciMLSensitivity
+    adjsol.stats
+catch err
+    @warn "adjoint step statistics not available" err
+    nothing
+end
+open(joinpath(dir, "stats.txt"), "w") do io
+    println(io, "fwd_naccept=", sol.stats.naccept); println(io, "fwd_nreject=", sol.stats.nreject); println(io, "fwd_nf=", sol.stats.nf)
+    if adj_stats !== nothing
+        println(io, "adj_naccept=", adj_stats.naccept); println(io, "adj_nreject=", adj_stats.nreject); println(io, "adj_nf=", adj_stats.nf)
+    end
+end
 write(joinpath(dir, "final_state.f32"), Float32.(vec(last(sol.u))))
 write(joinpath(dir, "du0.f32"), Float32.(vec(g[1])))
 write(joinpath(dir, "dp.f32"), Float32.(collect(g[2])))
