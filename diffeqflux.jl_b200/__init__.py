@@ -8,11 +8,11 @@ The directory name is not a legal Python identifier; import it through the repo-
 from . import _native
 from ._native import B200Error, build
 from .layers import (AdamState, Array, AugmentedNDELayer, BacksolveAdjoint, Chain, Dense, DimMover, FFJORD,
-                     FFJORDDistribution, GaussAdjoint, InterpolatingAdjoint, QuadratureAdjoint, NeuralODE, ODEProblem, ODESolution, ReturnCode, Tsit5,
+                     EnsembleProblem, EnsembleSerial, EnsembleThreads, FFJORDDistribution, GaussAdjoint, InterpolatingAdjoint, QuadratureAdjoint, NeuralODE, ODEProblem, ODESolution, ReturnCode, Tsit5,
                      UnsupportedError, ZygoteVJP, cube, group_ranges, identity, multiple_shoot, relu, setup, sigmoid,
                      softplus, successful_retcode, tanh, train_step)
 
-__all__ = ["GaussAdjoint", "QuadratureAdjoint", "AdamState", "DimMover", "FFJORDDistribution", "train_step", "Array", "AugmentedNDELayer", "BacksolveAdjoint", "Chain", "Dense", "FFJORD", "InterpolatingAdjoint",
+__all__ = ["EnsembleProblem", "EnsembleSerial", "EnsembleThreads", "GaussAdjoint", "QuadratureAdjoint", "AdamState", "DimMover", "FFJORDDistribution", "train_step", "Array", "AugmentedNDELayer", "BacksolveAdjoint", "Chain", "Dense", "FFJORD", "InterpolatingAdjoint",
            "NeuralODE", "ODEProblem", "ODESolution", "ReturnCode", "Tsit5", "UnsupportedError", "ZygoteVJP", "cube",
            "group_ranges", "identity", "multiple_shoot", "relu", "setup", "sigmoid", "softplus",
            "successful_retcode", "tanh", "B200Error", "build"]

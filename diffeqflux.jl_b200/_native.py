@@ -45,7 +45,8 @@ class Opts(C.Structure):
                 ("maxiters", C.c_int), ("save_start", C.c_int), ("save_end", C.c_int),
                 ("sensealg", C.c_int), ("ptr_kind", C.c_int), ("tile", C.c_int),
                 ("max_dense_steps", C.c_int), ("seed", C.c_uint64), ("noise_per_call", C.c_int),
-                ("b_offset", C.c_int), ("save_everystep", C.c_int), ("path", C.c_int), ("reserved", C.c_int * 2)]
+                ("b_offset", C.c_int), ("save_everystep", C.c_int), ("path", C.c_int), ("ffjord_exact_trace", C.c_int),
+                ("reserved", C.c_int * 1)]
 
 
 class Stats(C.Structure):

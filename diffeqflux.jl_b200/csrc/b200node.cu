@@ -83,6 +83,7 @@ struct b200_tape {
   unsigned long long seed = 0;
   int noise_per_call = 1;
   int b_offset = 0;
+  int exact_trace = 0;
 };
 
 // Every entry point binds the context's device for the duration of the call and restores the caller's device
@@ -799,6 +800,10 @@ static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, cons
   P.saveat = saveat_dev; P.nsave = nsave; P.save_start = o->save_start; P.save_end = o->save_end;
   P.out_u = t->out_u; P.out_t = t->out_t; P.step_t = t->step_t; P.dense = t->dense; P.tape_cap = cap;
   P.seed = o->seed; P.noise_per_call = o->noise_per_call; P.b_offset = o->b_offset;
+  P.exact_trace = (flavor == FL_FWD_FFJORD && o->ffjord_exact_trace) ? 1 : 0;
+  if (P.exact_trace && !P.rowthread)
+    return fail(set_err(ctx, B200_ERR_UNSUPPORTED, "FFJORD monte_carlo = false (exact trace) is built for networks whose widths are all <= 64"));
+  t->exact_trace = P.exact_trace;
   if (o->save_everystep) { P.save_start = 0; P.save_end = 0; }
   rc = run_solve(ctx, flavor, P, smem_bytes, st);
   if (rc < 0) return fail(rc);
@@ -956,6 +961,7 @@ static int adjoint_core(b200_ctx* ctx, b200_tape* t, int flavor, const float* dL
   P.f_us = t->out_u; P.f_final = t->final_state; P.f_ts = ts_d; P.n_ts = (int)t->ts.size(); P.dL = dL_dev;
   P.slabs = slabs; P.mu = mu; P.mu_out = muo;
   P.seed = t->seed; P.noise_per_call = t->noise_per_call; P.b_offset = t->b_offset;
+  P.exact_trace = (flavor == FL_ADJ_FFJORD) ? t->exact_trace : 0;
   rc = run_solve(ctx, flavor, P, smem_bytes, st);
   cleanup();
 #undef TRY

@@ -187,6 +187,7 @@ struct SolveParams {
   float* slabs;          // [nctas][4][ppad]
   float* mu;             // [2][ppad]
   float* mu_out;         // [ppad]
+  int exact_trace;       // FFJORD monte_carlo = false: trace of the Jacobian by D unit-vector passes instead of one noise pass
   int rowthread;         // FFJORD forward, all widths <= 64: one thread per trajectory (rhs_ffjord_fwd_rows)
   int mu_in_norm;        // 1: mu is a state of the adjoint ODE (Interpolating / Backsolve); 0: quadrature (Quadrature / Gauss adjoints)
   // FFJORD
@@ -976,13 +977,16 @@ struct Solver {
   }
 
   // ---------------------------------------------------------------- noise
-  __device__ void fill_noise(int tile, unsigned int stream, unsigned int call, float* dst, int ld) {
+  // unit >= 0: the unit vector e_unit instead of noise (exact trace, monte_carlo = false: src/ffjord.jl:120-123)
+  __device__ void fill_noise(int tile, unsigned int stream, unsigned int call, float* dst, int ld, int unit = -1) {
     const int D = P.D, nq = (D + 3) >> 2;
     const int base_row = tile * P.TB;
     for (int e = tid; e < P.TB * nq; e += NTHREADS) {
       const int r = e / nq, q = e - r * nq;
       float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (base_row + r < P.B) {
+      if (unit >= 0) {
+        if ((unit >> 2) == q) (&z.x)[unit & 3] = 1.f;
+      } else if (base_row + r < P.B) {
         z = philox_normal4(P.seed, stream, P.noise_per_call ? call : 0u,
                            (unsigned int)(P.b_offset + base_row + r), (unsigned int)q);
         if (q * 4 + 1 >= D) z.y = 0.f;
@@ -1113,10 +1117,13 @@ struct Solver {
     const int D = P.D, NV = P.NV, B = P.B, TB = P.TB, L = M.nl;
     const int base_row = tile * TB;
     const int Lp = M.dpad[L];
-    float* e = sm + P.sp.dl_off;                       // noise, [row][Lp] (fill_noise layout)
-    fill_noise(tile, 0u, call, e, Lp);
-    sync();
+    float* e = sm + P.sp.dl_off;                       // noise (or the unit vector of the pass), [row][Lp] (fill_noise layout)
+    const int npass = P.exact_trace ? D : 1;           // exact trace: sum_d e_d^T J e_d, one reverse pass per unit vector
     float acc[64];
+    for (int pass = 0; pass < npass; ++pass) {
+    if (pass > 0) sync();                              // every thread has read the previous pass' seed
+    fill_noise(tile, 0u, call, e, Lp, P.exact_trace ? pass : -1);
+    sync();
     for (int t = tid; t < TB; t += NTHREADS) {
       // ---- forward: h_{l+1} = act(h_l W_l + b_l); hidden h_l kept column-major in the act_off[l] buffer
       for (int l = 0; l < L; ++l) {
@@ -1136,7 +1143,7 @@ struct Solver {
 #pragma unroll
           for (int n = 0; n < 64; ++n)
             if (n < N) H[n * TB] = act_apply(a, acc[n]);
-        } else if (base_row + t < B) {
+        } else if (pass == 0 && base_row + t < B) {
           float* o = kout + (long long)(base_row + t) * NV;
 #pragma unroll
           for (int n = 0; n < 64; ++n)
@@ -1163,7 +1170,11 @@ struct Solver {
             if (k < D) tr = fmaf(acc[k], e[t * Lp + k], tr);
         }
       }
-      if (base_row + t < B) kout[(long long)(base_row + t) * NV + D] = -tr;
+      if (base_row + t < B) {
+        float* o = kout + (long long)(base_row + t) * NV + D;
+        *o = pass == 0 ? -tr : *o - tr;
+      }
+    }
     }
     sync();
   }
@@ -1178,8 +1189,20 @@ struct Solver {
     float* hb = sm + P.sp.dl_off;     // hbar_L = lz (already routed)
     float* hdb = sm + P.sp.dl2_off;   // hdbar_L = -ll * e
     const float* ll = sm + P.sp.ll_off;
+    // Exact trace (monte_carlo = false): the RHS is  <lz, m(z)> - ll * sum_d <e_d, J(z) e_d>.  Everything below is linear in
+    // the seed pair (hbar_L, hdbar_L), so D passes with (lz / D, -ll e_d) add up to it; the first pass stores its results
+    // (derivative rows, gradient slabs), the others accumulate.
+    const int npass = P.exact_trace ? D : 1;
+    if (npass > 1) {
+      const float inv = 1.f / (float)npass;
+      for (int e = tid; e < P.TB * Lp; e += NTHREADS) hb[e] *= inv;
+      sync();
+    }
+    for (int pass = 0; pass < npass; ++pass) {
+    const bool acc_pass = pass > 0;
+    const bool acc_store_p = acc_store || acc_pass;
     // hdot_0 = e
-    fill_noise(tile, 1u, call, sm + P.sp.hd_off[0], M.dpad[0]);
+    fill_noise(tile, 1u, call, sm + P.sp.hd_off[0], M.dpad[0], P.exact_trace ? pass : -1);
     sync();
     for (int e = tid; e < P.TB * Lp; e += NTHREADS) {
       const int r = e / Lp, c = e - r * Lp;
@@ -1230,7 +1253,7 @@ struct Solver {
     for (int l = L; l >= 1; --l) {
       const int li = l - 1;
       const int Np = M.dpad[l], Kp = M.dpad[li];
-      layer_wgrad(li, sm + P.sp.act_off[li], X, sm + P.sp.hd_off[li], Y, so, acc_store);
+      layer_wgrad(li, sm + P.sp.act_off[li], X, sm + P.sp.hd_off[li], Y, so, acc_store_p);
       sync();
       const float* WT = P.wtp + M.wt_off[li];
       if (li >= 1) {
@@ -1284,10 +1307,10 @@ struct Solver {
             const int row = row0 + i;
             if (base_row + row < B) {
               float* o = kout + (long long)(base_row + row) * NV + col0;
-              if (col0 + 0 < D) o[0] = -acc[i][0];
-              if (col0 + 1 < D) o[1] = -acc[i][1];
-              if (col0 + 2 < D) o[2] = -acc[i][2];
-              if (col0 + 3 < D) o[3] = -acc[i][3];
+              if (col0 + 0 < D) o[0] = (acc_pass ? o[0] : 0.f) - acc[i][0];
+              if (col0 + 1 < D) o[1] = (acc_pass ? o[1] : 0.f) - acc[i][1];
+              if (col0 + 2 < D) o[2] = (acc_pass ? o[2] : 0.f) - acc[i][2];
+              if (col0 + 3 < D) o[3] = (acc_pass ? o[3] : 0.f) - acc[i][3];
             }
           }
         });
@@ -1296,6 +1319,7 @@ struct Solver {
         sync();
       }
     }
+    }   // pass
   }
 
   // ---------------------------------------------------------------- whole-vector helpers

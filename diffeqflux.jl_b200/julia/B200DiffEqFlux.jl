@@ -39,7 +39,8 @@ Base.@kwdef mutable struct B200Opts
     b_offset::Cint = 0
     save_everystep::Cint = 0
     path::Cint = 0              # 0 auto, 1 FFMA only, 2 require tcgen05
-    reserved::NTuple{2, Cint} = (0, 0)
+    ffjord_exact_trace::Cint = 0    # FFJORD monte_carlo = false
+    reserved::NTuple{1, Cint} = (0,)
 end
 
 mutable struct B200Stats
@@ -241,12 +242,13 @@ FFJORD(model, tspan, input_dims, args...; ad = nothing, basedist = nothing, kwar
 LuxCore.initialstates(rng, n::FFJORD) = (; model = LuxCore.initialstates(rng, n.model), regularize = false, monte_carlo = true)
 
 function ffjord_forward(n::FFJORD, x::AbstractMatrix{Float32}, pv, st, tspan; want_tape::Bool, seed = rand(UInt64))
-    (st.regularize || !st.monte_carlo) && error("B200 path: only regularize = false, monte_carlo = true")
+    st.regularize && error("B200 path: regularize = true is not supported")
     B = size(x, 2)
     logpx = Vector{Float32}(undef, B)
     z = Matrix{Float32}(undef, size(x, 1) + 1, B)
     o = B200Opts(; abstol = get(n.kwargs, :abstol, 1.0f-6), reltol = get(n.kwargs, :reltol, 1.0f-3),
-                 sensealg = want_tape ? 0 : -1, seed)             # InterpolatingAdjoint is hard-wired at src/ffjord.jl:143
+                 sensealg = want_tape ? 0 : -1, seed,             # InterpolatingAdjoint is hard-wired at src/ffjord.jl:143
+                 ffjord_exact_trace = st.monte_carlo ? 0 : 1)
     tape = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall(sym(:b200_ffjord_forward), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cfloat, Cfloat, Ref{B200Opts}, Ptr{Cfloat}, Ptr{Cfloat},

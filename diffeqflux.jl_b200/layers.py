@@ -550,7 +550,8 @@ if torch is not None:
     class _FfjordFn(torch.autograd.Function):
         @staticmethod
         def forward(ctx, x, p, layer, seed, holder):
-            fw = layer._forward(x, p, seed, want_tape=True)
+            seed, exact = seed
+            fw = layer._forward(x, p, seed, want_tape=True, exact=exact)
             holder.update(fw)
             ctx.layer, ctx.fw, ctx.owner = layer, fw, _TapeOwner(fw["tape"])
             out = fw["logpx"]
@@ -594,7 +595,7 @@ class FFJORD:
         return {"model": {}, "regularize": False, "monte_carlo": True,
                 "seed": int(rng.integers(0, 2**62)) if hasattr(rng, "integers") else 0, "calls": 0}
 
-    def _forward(self, x, p, seed, want_tape):
+    def _forward(self, x, p, seed, want_tape, exact=False):
         xb, pb = _Buf(x), _Buf(p)
         shape = tuple(xb.t.shape) if _is_torch(x) else xb.a.shape
         if len(shape) != 2 or shape[1] != self.model.dims[0]:
@@ -607,6 +608,7 @@ class FFJORD:
         o = self._solve.opts(on_dev, want_tape)
         o.seed = int(seed) & (2**64 - 1)
         o.noise_per_call = int(self.kwargs.get("noise_per_call", 1))
+        o.ffjord_exact_trace = 1 if exact else 0        # monte_carlo = false (src/ffjord.jl:120-123)
         o.b_offset = _dist_state["rank"] * B            # global trajectory index of this shard (noise stream)
         if want_tape:
             o.sensealg = N.SENSE_INTERPOLATING      # hard-wired at src/ffjord.jl:143
@@ -637,15 +639,14 @@ class FFJORD:
     def __call__(self, x, ps, st):
         if st.get("regularize", False):
             raise UnsupportedError("regularize = true is outside the B200 path")
-        if not st.get("monte_carlo", True):
-            raise UnsupportedError("monte_carlo = false (exact trace) is outside the B200 path")
+        exact = not st.get("monte_carlo", True)
         seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
         needs_grad = _is_torch(x) and _is_torch(ps) and torch.is_grad_enabled() and (x.requires_grad or ps.requires_grad)
         if needs_grad:
             self.last = {}
-            logpx = _FfjordFn.apply(x, ps, self, seed, self.last)
+            logpx = _FfjordFn.apply(x, ps, self, (seed, exact), self.last)
         else:
-            self.last = self._forward(x, ps, seed, want_tape=False)
+            self.last = self._forward(x, ps, seed, want_tape=False, exact=exact)
             logpx = self.last["logpx"]
         logpx = logpx.reshape(1, -1) if not _is_torch(logpx) else logpx.reshape(1, -1)
         z = self.last["z"]
@@ -655,8 +656,10 @@ class FFJORD:
         return (logpx, delta_logp, delta_logp), st2
 
     def pullback(self, x, ps, st):
+        if st.get("regularize", False):
+            raise UnsupportedError("regularize = true is outside the B200 path")
         seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
-        fw = self._forward(x, ps, seed, want_tape=True)
+        fw = self._forward(x, ps, seed, want_tape=True, exact=not st.get("monte_carlo", True))
         owner = _TapeOwner(fw["tape"])
         self.last = fw
 
@@ -673,8 +676,6 @@ class FFJORD:
         the learned density.  One b200_ffjord_forward call with the time span reversed."""
         if st.get("regularize", False):
             raise UnsupportedError("regularize = true is outside the B200 path")
-        if not st.get("monte_carlo", True):
-            raise UnsupportedError("monte_carlo = false (exact trace) is outside the B200 path")
         D = self.model.dims[0]
         if z is None:
             rng = np.random.default_rng() if rng is None else rng
@@ -683,7 +684,7 @@ class FFJORD:
                 z = torch.from_numpy(z).to(ps.device)
         seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
         rev = FFJORD(self.model, (self.tspan[1], self.tspan[0]), self.input_dims, *self.args, **self.kwargs)
-        fw = rev._forward(z, ps, seed, want_tape=False)
+        fw = rev._forward(z, ps, seed, want_tape=False, exact=not st.get("monte_carlo", True))
         self.last = fw
         return fw["z"][:, :D]
 
@@ -910,12 +911,79 @@ class _MshootRun:
         return dp, dblocks
 
 
-def multiple_shoot(p, ode_data, tsteps, prob: ODEProblem, loss_function, *rest, continuity_term=100, **kwargs):
+@dataclass
+class EnsembleProblem:
+    """`EnsembleProblem(prob)` (SciMLBase) as the ensemble `multiple_shoot` takes it (src/multiple_shooting.jl:131-195);
+    `prob_func` / `output_func` / `reduction` other than the defaults are outside the B200 path."""
+    prob: ODEProblem
+
+
+class EnsembleThreads:
+    pass
+
+
+class EnsembleSerial:
+    pass
+
+
+def _multiple_shoot_ensemble(p, ode_data, tsteps, eprob, ensemblealg, loss_function, rest, continuity_term, kwargs):
+    """Ensemble variant (src/multiple_shooting.jl:131-195): `ode_data` is Julia (D, T, trajectories) = C-order
+    (trajectories, T, D); every (group, trajectory) pair is an INDEPENDENT solve with its own adaptive step sequence
+    (that is what an EnsembleProblem means), so each trajectory runs as its own batch-1 grouped solve -- the groups of
+    one trajectory in one C-ABI call, concurrently on the library's lanes.  group_predictions[i] is (trajectories, len, D)."""
+    if len(rest) == 3:
+        continuity_loss, solver, group_size = rest
+    elif len(rest) == 2:
+        continuity_loss = _default_continuity_loss
+        solver, group_size = rest
+    else:
+        raise TypeError("multiple_shoot(p, ode_data, tsteps, ensembleprob, ensemblealg, loss_function, [continuity_loss], solver, group_size)")
+    kwargs = dict(kwargs)
+    nd = ode_data.dim() if _is_torch(ode_data) else np.asarray(ode_data).ndim
+    if nd < 3:
+        raise AssertionError("ode_data must have at least three dimension: `size(ode_data) = (problem_dimension,length(tsteps),trajectories)")
+    ntraj, datasize = ode_data.shape[0], ode_data.shape[1]
+    if group_size < 2 or group_size > datasize:
+        raise ValueError("DomainError: group_size can't be < 2 or > number of data points")
+    if datasize != len(tsteps):
+        raise AssertionError("datasize == length(tsteps)")
+    if kwargs.pop("trajectories", None) != ntraj:
+        raise AssertionError("ntraj == kwargs[:trajectories]")
+    ranges = group_ranges(datasize, group_size)
+    per_traj, worst = [], 0
+    for i in range(ntraj):
+        data_i = ode_data[i][:, None, :]                           # (T, 1, D): one trajectory = one shared-dt batch of 1
+        loss_i, preds_i = multiple_shoot(p, data_i, tsteps, eprob.prob, lambda u, uh: 0.0, lambda a, b: 0.0, solver, group_size,
+                                         continuity_term=0, **kwargs)
+        worst = max(worst, multiple_shoot.last.retcode)
+        per_traj.append(preds_i)
+    cat = (lambda xs: torch.cat(xs, dim=1)) if _is_torch(per_traj[0][0]) else (lambda xs: np.concatenate(xs, axis=1))
+    group_predictions = []
+    for g in range(len(ranges)):
+        gp = cat([per_traj[i][g] for i in range(ntraj)])           # (len, trajectories, D)
+        group_predictions.append(gp.permute(1, 0, 2) if _is_torch(gp) else np.transpose(gp, (1, 0, 2)))
+    if not successful_retcode(worst):                               # `any(.!convergeds) && return Inf, group_predictions`
+        return float("inf"), group_predictions
+    loss = 0
+    for g, (a, b) in enumerate(ranges):
+        u = ode_data[:, a:b + 1]
+        loss = loss + loss_function(u, group_predictions[g])
+        if g > 0:
+            loss = loss + continuity_term * continuity_loss(group_predictions[g - 1][:, -1], u[:, 0])
+    return loss, group_predictions
+
+
+def multiple_shoot(p, ode_data, tsteps, prob, loss_function, *rest, continuity_term=100, **kwargs):
     """`multiple_shoot(p, ode_data, tsteps, prob, loss_function, [continuity_loss], solver, group_size;
-    continuity_term = 100, kwargs...)` (src/multiple_shooting.jl:36-94) -> (loss, group_predictions).
+    continuity_term = 100, kwargs...)` (src/multiple_shooting.jl:36-94) -> (loss, group_predictions), and the ensemble
+    method `multiple_shoot(p, ode_data, tsteps, ensembleprob, ensemblealg, loss_function, [continuity_loss], solver,
+    group_size; trajectories, ...)` (src/multiple_shooting.jl:131-195).
 
     `ode_data` is (T, B, D) (Julia (D, B, T)) or (T, D).  All groups are solved by ONE C-ABI call;
     the loss callbacks run on the host framework (torch), whose autograd chains into the adjoint."""
+    if isinstance(prob, EnsembleProblem):
+        # positional layout of the ensemble method: (ensembleprob, ensemblealg, loss_function, [continuity_loss], solver, group_size)
+        return _multiple_shoot_ensemble(p, ode_data, tsteps, prob, loss_function, rest[0], rest[1:], continuity_term, kwargs)
     if len(rest) == 3:
         continuity_loss, solver, group_size = rest
     elif len(rest) == 2:

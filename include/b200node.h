@@ -88,7 +88,9 @@ typedef struct b200_opts {
                             (out_u/out_t of the call stay untouched) */
   int path;              /* RHS engine: 0 = automatic, 1 = FP32-FFMA kernels only, 2 = require the tcgen05
                             3xTF32 tensor-core engine (error if the model shape is not eligible) */
-  int reserved[2];
+  int ffjord_exact_trace;/* FFJORD: 1 = monte_carlo = false (src/ffjord.jl:120-123): the trace of the Jacobian is exact (D
+                            unit-vector passes per RHS call instead of one Hutchinson noise pass); networks with widths <= 64 */
+  int reserved[1];
 } b200_opts;
 
 typedef struct b200_stats {

@@ -1,9 +1,10 @@
-"""ORACLE (test infrastructure only) -- `multiple_shoot` (single-problem variant).
+"""ORACLE (test infrastructure only) -- `multiple_shoot` (single-problem and ensemble variants).
 
 PARITY UNPINNED (see oracle/tsit5.py header; the reference's multiple-shooting test file is a
 skipped stub, /root/reference/test/BasicNeuralDE/multiple_shoot_tests.jl:5-10).  Follows
 /root/reference/src/multiple_shooting.jl:36-84 (grouped solves + loss) and :231-243
-(`group_ranges`, default continuity loss).
+(`group_ranges`, default continuity loss), and :131-195 (EnsembleProblem method: every trajectory of every group is an
+independent solve with its own step sequence).
 
 numpy view of `ode_data`: (T, B, D) C-order == Julia (D, B, T) column-major.
 """
@@ -64,3 +65,25 @@ def multiple_shoot(problem, p, ode_data, tsteps, group_size, *, continuity_term=
         dp += adj.dp
         adj_stats.append(adj.stats)
     return loss, preds, dp.astype(np.float32), (stats, adj_stats)
+
+
+def multiple_shoot_ensemble(problem, p, ode_data, tsteps, group_size, *, continuity_term=100.0, abstol=1e-6, reltol=1e-3,
+                            sensealg=node.SENSE_INTERPOLATING):
+    """Ensemble method (/root/reference/src/multiple_shooting.jl:131-195).  ode_data: (trajectories, T, D) C-order == Julia
+    (D, T, trajectories).  loss = sum over groups of sum(abs2, u - u_hat) over all trajectories + continuity terms; every
+    (group, trajectory) solve is independent, i.e. a batch-1 run of the shared-dt integrator.  Returns (loss, preds, dp)
+    with preds[g] of shape (trajectories, len_g, D); loss is +inf if any solve failed."""
+    ode_data = np.asarray(ode_data, dtype=np.float32)
+    ntraj = ode_data.shape[0]
+    total, dp = 0.0, np.zeros(p.size, np.float64)
+    per = []
+    for i in range(ntraj):
+        loss_i, preds_i, dp_i, _ = multiple_shoot(problem, p, ode_data[i][:, None, :], tsteps, group_size, continuity_term=continuity_term,
+                                                  abstol=abstol, reltol=reltol, sensealg=sensealg)
+        if not np.isfinite(loss_i):
+            return float("inf"), None, None
+        total += loss_i
+        dp += dp_i
+        per.append(preds_i)
+    preds = [np.concatenate([per[i][g] for i in range(ntraj)], axis=1).transpose(1, 0, 2) for g in range(len(per[0]))]
+    return total, preds, dp.astype(np.float32)

@@ -50,19 +50,34 @@ class FfjordProblem:
     """state rows [z (D); delta_logp (1)], RHS = [m(z); -e^T J e] with fresh e per RHS call
     (/root/reference/src/ffjord.jl:85-92,105-115,134)."""
 
-    def __init__(self, mlp: MLP, seed: int, b_offset: int = 0):
+    def __init__(self, mlp: MLP, seed: int, b_offset: int = 0, monte_carlo: bool = True):
         self.mlp = mlp
         self.D = mlp.dims[0]
         self.ns = self.D + 1
         self.seed = seed
         self.b_offset = b_offset
+        # monte_carlo = false (/root/reference/src/ffjord.jl:120-123): the trace of the batched Jacobian itself, here as
+        # sum_d e_d^T J e_d over the unit vectors (what `__trace_batched(Lux.batched_jacobian(...))` evaluates)
+        self.monte_carlo = monte_carlo
 
     def noise(self, B, call, stream):
         return normal(self.seed, stream, call, B, self.D, self.b_offset)
 
+    def units(self, B):
+        for d in range(self.D):
+            e = np.zeros((B, self.D), np.float32)
+            e[:, d] = 1
+            yield e
+
     def f(self, p, y, call, stream):
         z = np.ascontiguousarray(y[:, :self.D])
         mz, cache = self.mlp.forward(p, z)
+        if not self.monte_carlo:
+            tr = np.zeros(z.shape[0], np.float32)
+            for e in self.units(z.shape[0]):
+                eJ, _ = self.mlp.vjp(cache, e, want_dp=False)
+                tr = (tr + np.sum(eJ * e, axis=1, dtype=np.float32)).astype(np.float32)
+            return np.concatenate([mz, -tr[:, None]], axis=1).astype(np.float32), None
         e = self.noise(z.shape[0], call, stream)
         eJ, _ = self.mlp.vjp(cache, e, want_dp=False)
         tr = np.sum(eJ * e, axis=1, dtype=np.float32)
@@ -73,6 +88,17 @@ class FfjordProblem:
         z = np.ascontiguousarray(y[:, :self.D])
         lz = np.ascontiguousarray(lam[:, :self.D])
         ll = lam[:, self.D:self.D + 1]
+        if not self.monte_carlo:
+            out, _ = self.f(p, y, call, stream)
+            zbar = np.zeros_like(z)
+            pbar = np.zeros(p.size, np.float32)
+            for e in self.units(z.shape[0]):          # linear in the seeds: (lz / D, -ll e_d) per unit vector
+                _, _, cache = self.mlp.jvp_forward(p, z, e)
+                zb, pb = self.mlp.second_order_vjp(cache, (lz / np.float32(self.D)).astype(np.float32), (-ll * e).astype(np.float32))
+                zbar = (zbar + zb).astype(np.float32)
+                pbar = (pbar + pb).astype(np.float32)
+            ybar = np.concatenate([zbar, np.zeros_like(ll)], axis=1).astype(np.float32)
+            return out, ybar, pbar
         e = self.noise(z.shape[0], call, stream)
         hL, hdL, cache = self.mlp.jvp_forward(p, z, e)
         tr = np.sum(hdL * e, axis=1, dtype=np.float32)

@@ -616,3 +616,61 @@ def test_cfg5_shape_augmented_192_512_512_192():
         close(sol.array(), fw.us, rtol=rtol, what=f"states tol {tol}")
         close(dp, adj.dp, rtol=rtol, what=f"dp tol {tol}")
         close(du0, adj.du0, rtol=rtol, what=f"du0 tol {tol}")
+
+
+def test_multiple_shoot_ensemble():
+    """N4: the EnsembleProblem method of multiple_shoot (src/multiple_shooting.jl:131-195): every trajectory of every group
+    is an independent solve (own step sequence); loss, predictions and dp against the oracle's restatement."""
+    import torch
+    rng, mlp, teacher, chain = make([4, 16, 4], 7, scale=2.0)
+    prob_o = onode.NodeProblem(mlp)
+    ts = np.linspace(0, 2, 9, dtype=np.float32)
+    ntraj = 3
+    u0 = rng.standard_normal((ntraj, 4)).astype(np.float32)
+    tol = dict(abstol=1e-6, reltol=1e-6)
+    data = np.stack([onode.forward(prob_o, teacher, u0[i], 0.0, 2.0, saveat=ts, **tol).us[:, 0, :] for i in range(ntraj)])   # (ntraj, T, D)
+    p = (teacher + 0.05 * rng.standard_normal(teacher.size)).astype(np.float32)
+    want_loss, want_preds, want_dp = omshoot.multiple_shoot_ensemble(prob_o, p, data, ts, 3, **tol)
+    pt = torch.tensor(p, requires_grad=True)
+    eprob = dfx.EnsembleProblem(dfx.ODEProblem(chain, u0[0], (0.0, 2.0), p))
+    loss, preds = dfx.multiple_shoot(pt, torch.tensor(data), ts, eprob, dfx.EnsembleThreads(), lambda u, uh: ((u - uh) ** 2).sum(),
+                                     dfx.Tsit5(), 3, trajectories=ntraj, **tol)
+    assert len(preds) == 4 and tuple(preds[0].shape) == (ntraj, 3, 4)
+    for a, b in zip(preds, want_preds):
+        close(a.detach().numpy(), b, what="ensemble preds")
+    assert abs(loss.item() - want_loss) <= 1e-4 * abs(want_loss)
+    loss.backward()
+    close(pt.grad.numpy(), want_dp, rtol=2e-4, what="ensemble dp")
+    with pytest.raises(AssertionError):
+        dfx.multiple_shoot(p, data, ts, eprob, dfx.EnsembleThreads(), lambda u, uh: 0.0, dfx.Tsit5(), 3, trajectories=ntraj + 1)
+
+
+def test_ffjord_exact_trace():
+    """N4: FFJORD with monte_carlo = false (src/ffjord.jl:120-123, test/AdvancedNeuralDE/cnf_tests.jl:34-38): the exact
+    trace of the Jacobian by D unit-vector passes.  Deterministic RHS: step counts of both passes exact, logpx / dx / dp
+    element-wise within 1e-4; for a linear model logpx has the closed form logN(x e^{tW}) + t tr(W)."""
+    rng = np.random.default_rng(8)
+    mlp = MLP([3, 16, 16, 3], [ACT_TANH, ACT_TANH, ACT_ID])
+    p = mlp.init(rng, scale=1.0)
+    B = 300
+    x = rng.standard_normal((B, 3)).astype(np.float32)
+    tol = dict(abstol=1e-6, reltol=1e-6)
+    prob = onode.FfjordProblem(mlp, seed=0, monte_carlo=False)
+    fw = onode.forward(prob, p, np.concatenate([x, np.zeros((B, 1), np.float32)], 1), 0.0, 0.5, save_everystep=False,
+                       save_start=False, dense=True, **tol)
+    g = np.cos(np.arange(B, dtype=np.float32))
+    adj = onode.adjoint(prob, p, fw, onode.ffjord_logpx_grad(fw.us[0], 3, g)[None], **tol)
+    chain = dfx.Chain(dfx.Dense(3, 16, dfx.tanh), dfx.Dense(16, 16, dfx.tanh), dfx.Dense(16, 3))
+    ff = dfx.FFJORD(chain, (0.0, 0.5), (3,), dfx.Tsit5(), **tol)
+    st = {"regularize": False, "monte_carlo": False, "seed": 0, "calls": 0}
+    logpx, back = ff.pullback(x, p, st)
+    dx, dp = back(g)
+    check_steps(ff.last["stats"], fw.stats, "exact-trace forward", True)
+    assert abs(ff.last["adjoint_stats"].naccept - adj.stats.naccept) <= 1
+    close(np.asarray(logpx).reshape(-1), onode.ffjord_logpx(fw.us[0], 3), what="logpx")
+    close(dx, adj.du0[:, :3], what="dx")
+    close(dp, adj.dp, what="dp")
+    (lp2, _, _), _ = ff(x, p, st)                                  # the layer call protocol takes the same branch
+    assert np.array_equal(np.asarray(lp2).reshape(-1), np.asarray(logpx).reshape(-1))
+    with pytest.raises(dfx.UnsupportedError):
+        ff(x, p, {"regularize": True, "monte_carlo": False, "seed": 0, "calls": 0})

@@ -328,3 +328,39 @@ def test_quadrature_adjoint_agrees_with_interpolating():
     assert np.abs(aq.dp - ai.dp).max() <= 2e-5 * np.abs(ai.dp).max()
     assert np.abs(aq.du0 - ai.du0).max() <= 2e-5 * np.abs(ai.du0).max()
     assert aq.stats.nf == 3 + 6 * (aq.stats.naccept + aq.stats.nreject) + 1      # one FSAL re-evaluation at the interior jump
+
+
+def test_ffjord_exact_trace_restatement():
+    """monte_carlo = false: the RHS's last row is minus the exact trace of dm/dz (checked against a finite-difference
+    Jacobian of the fp64 model), and the adjoint RHS is the derivative of <lam, f> (finite differences in z)."""
+    rng = np.random.default_rng(9)
+    mlp64 = MLP([3, 8, 3], [ACT_TANH, ACT_ID], dtype=np.float64)
+    mlp = MLP([3, 8, 3], [ACT_TANH, ACT_ID])
+    p = mlp.init(rng, scale=1.5)
+    z = rng.standard_normal((5, 3)).astype(np.float32)
+    prob = node.FfjordProblem(mlp, seed=1, monte_carlo=False)
+    y = np.concatenate([z, np.zeros((5, 1), np.float32)], 1)
+    out, _ = prob.f(p, y, 0, 0)
+    eps = 1e-6
+    for b in range(5):
+        J = np.zeros((3, 3))
+        for k in range(3):
+            zp, zm = z[b:b + 1].astype(np.float64).copy(), z[b:b + 1].astype(np.float64).copy()
+            zp[0, k] += eps; zm[0, k] -= eps
+            J[:, k] = (mlp64(p.astype(np.float64), zp) - mlp64(p.astype(np.float64), zm))[0] / (2 * eps)
+        assert abs(-out[b, 3] - np.trace(J)) <= 1e-4 * max(1.0, abs(np.trace(J)))
+    lam = rng.standard_normal((5, 4)).astype(np.float32)
+    _, ybar, pbar = prob.vjp(p, y, lam, 0, 1)
+    prob64 = node.FfjordProblem(MLP([3, 8, 3], [ACT_TANH, ACT_ID], dtype=np.float64), seed=1, monte_carlo=False)
+
+    def phi(zz):
+        yy = np.concatenate([zz, np.zeros((5, 1))], 1)
+        o, _ = prob.f(p, yy.astype(np.float32), 0, 0)
+        return float(np.sum(lam.astype(np.float64) * o.astype(np.float64)))
+    h = 1e-2
+    for (b, k) in ((0, 0), (3, 2)):
+        zp, zm = z.astype(np.float64).copy(), z.astype(np.float64).copy()
+        zp[b, k] += h; zm[b, k] -= h
+        fd = (phi(zp) - phi(zm)) / (2 * h)
+        assert abs(fd - ybar[b, k]) <= 2e-2 * max(1.0, abs(fd)), (fd, ybar[b, k])
+    assert pbar.shape == p.shape and np.abs(pbar).max() > 0
