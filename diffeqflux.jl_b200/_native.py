@@ -46,7 +46,7 @@ class Opts(C.Structure):
                 ("sensealg", C.c_int), ("ptr_kind", C.c_int), ("tile", C.c_int),
                 ("max_dense_steps", C.c_int), ("seed", C.c_uint64), ("noise_per_call", C.c_int),
                 ("b_offset", C.c_int), ("save_everystep", C.c_int), ("path", C.c_int), ("ffjord_exact_trace", C.c_int),
-                ("reserved", C.c_int * 1)]
+                ("ffjord_regularize", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -89,6 +89,7 @@ _SIGNATURES = {
     "b200_ffjord_forward": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_float, C.c_float, C.POINTER(Opts),
                                       _fp, _fp, C.POINTER(Stats), C.POINTER(_vp)]),
     "b200_ffjord_adjoint": (C.c_int, [_vp, _vp, _vp, _fp, C.POINTER(Opts), _fp, _fp, C.POINTER(Stats)]),
+    "b200_ffjord_adjoint_state": (C.c_int, [_vp, _vp, _vp, _fp, _fp, C.POINTER(Opts), _fp, _fp, C.POINTER(Stats)]),
     "b200_group_ranges": (C.c_int, [C.c_int, C.c_int, _ip, _ip, C.c_int]),
     "b200_mshoot_forward": (C.c_int, [_vp, _vp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _ip, _ip,
                                       C.POINTER(Opts), _fp, C.POINTER(Stats), C.POINTER(_vp)]),

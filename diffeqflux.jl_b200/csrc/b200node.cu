@@ -84,6 +84,7 @@ struct b200_tape {
   int noise_per_call = 1;
   int b_offset = 0;
   int exact_trace = 0;
+  int regularize = 0;
 };
 
 // Every entry point binds the context's device for the duration of the call and restores the caller's device
@@ -385,10 +386,10 @@ static bool tc_eligible(const MlpDesc& m, int flavor) {
 }
 
 // logpx = -sum(z^2)/2 - D/2 log(2 pi) - delta_logp      (src/ffjord.jl:171-176)
-__global__ void ffjord_logpx_kernel(const float* __restrict__ zend, int B, int D, float* __restrict__ logpx) {
+__global__ void ffjord_logpx_kernel(const float* __restrict__ zend, int B, int D, int NS, float* __restrict__ logpx) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const float* z = zend + (long long)b * (D + 1);
+  const float* z = zend + (long long)b * NS;
   float s = 0.f;
   for (int d = 0; d < D; ++d) s = fmaf(z[d], z[d], s);
   logpx[b] = -s / 2.f - (float)(D / 2.0 * 1.8378770664093453) - z[D];
@@ -398,14 +399,19 @@ __global__ void add_into_kernel(float* __restrict__ dst, const float* __restrict
   if (i < n) dst[i] += src[i];
 }
 // cotangent of the end state from the cotangent of logpx
-__global__ void ffjord_seed_kernel(const float* __restrict__ zend, const float* __restrict__ g, int B,
-                                   int D, float* __restrict__ dL) {
+// (g: cotangent of logpx or null; gz: cotangent of the end state itself or null)
+__global__ void ffjord_seed_kernel(const float* __restrict__ zend, const float* __restrict__ g,
+                                   const float* __restrict__ gz, int B, int D, int NS, float* __restrict__ dL) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const float* z = zend + (long long)b * (D + 1);
-  float* o = dL + (long long)b * (D + 1);
-  for (int d = 0; d < D; ++d) o[d] = -z[d] * g[b];
-  o[D] = -g[b];
+  const float* z = zend + (long long)b * NS;
+  float* o = dL + (long long)b * NS;
+  const float gb = g ? g[b] : 0.f;
+  for (int c = 0; c < NS; ++c) {
+    float v = c < D ? -z[c] * gb : (c == D ? -gb : 0.f);
+    if (gz) v += gz[(long long)b * NS + c];
+    o[c] = v;
+  }
 }
 // du0 (first d_in of NV columns) from the final adjoint state
 __global__ void extract_cols_kernel(const float* __restrict__ src, int B, int NV, int ncols,
@@ -714,7 +720,7 @@ static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, cons
                         b200_tape** tape_out) {
   const MlpDesc& m = model->m;
   const int D = m.dims[0];
-  const int NS = (flavor == FL_FWD_FFJORD) ? D + 1 : D;
+  const int NS = (flavor == FL_FWD_FFJORD) ? D + (o->ffjord_regularize ? 3 : 1) : D;
   b200_tape* t = new b200_tape();
   ctx->tapes.push_back(t);
   t->ctx = ctx; t->m = m; t->fwd_flavor = flavor; t->sensealg = o->sensealg;
@@ -804,6 +810,8 @@ static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, cons
   if (P.exact_trace && !P.rowthread)
     return fail(set_err(ctx, B200_ERR_UNSUPPORTED, "FFJORD monte_carlo = false (exact trace) is built for networks whose widths are all <= 64"));
   t->exact_trace = P.exact_trace;
+  P.regularize = (flavor == FL_FWD_FFJORD && o->ffjord_regularize) ? 1 : 0;
+  t->regularize = P.regularize;
   if (o->save_everystep) { P.save_start = 0; P.save_end = 0; }
   rc = run_solve(ctx, flavor, P, smem_bytes, st);
   if (rc < 0) return fail(rc);
@@ -962,6 +970,7 @@ static int adjoint_core(b200_ctx* ctx, b200_tape* t, int flavor, const float* dL
   P.slabs = slabs; P.mu = mu; P.mu_out = muo;
   P.seed = t->seed; P.noise_per_call = t->noise_per_call; P.b_offset = t->b_offset;
   P.exact_trace = (flavor == FL_ADJ_FFJORD) ? t->exact_trace : 0;
+  P.regularize = (flavor == FL_ADJ_FFJORD) ? t->regularize : 0;
   rc = run_solve(ctx, flavor, P, smem_bytes, st);
   cleanup();
 #undef TRY
@@ -1043,11 +1052,11 @@ extern "C" int b200_ffjord_forward(b200_ctx* ctx, const b200_model* model, const
       float* lp_d = nullptr;
       if (o.ptr_kind == B200_PTR_DEVICE) lp_d = logpx; else { e = dalloc(ctx, &lp_d, (size_t)B); temps.push_back(lp_d); }
       if (e == cudaSuccess) {
-        ffjord_logpx_kernel<<<(B + 255) / 256, 256, 0, ctx->stream>>>(t->final_state, B, D, lp_d);
+        ffjord_logpx_kernel<<<(B + 255) / 256, 256, 0, ctx->stream>>>(t->final_state, B, D, t->NS, lp_d);
         if (o.ptr_kind == B200_PTR_HOST) from_device(ctx, logpx, lp_d, (size_t)B, B200_PTR_HOST);
       }
     }
-    if (z_out) from_device(ctx, z_out, t->final_state, (size_t)B * (D + 1), o.ptr_kind);
+    if (z_out) from_device(ctx, z_out, t->final_state, (size_t)B * t->NS, o.ptr_kind);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = set_err(ctx, B200_ERR_CUDA, "ffjord output: %s", cudaGetErrorString(e));
     if (tape && o.sensealg != B200_SENSE_NONE && e == cudaSuccess) *tape = t;
@@ -1060,22 +1069,30 @@ extern "C" int b200_ffjord_forward(b200_ctx* ctx, const b200_model* model, const
 extern "C" int b200_ffjord_adjoint(b200_ctx* ctx, const b200_model* model, b200_tape* tape,
                                    const float* dL_dlogpx, const b200_opts* o, float* dx, float* dp,
                                    b200_stats* stats) {
+  if (ctx && !dL_dlogpx) return set_err(ctx, B200_ERR_ARG, "null tape/dL_dlogpx");
+  return b200_ffjord_adjoint_state(ctx, model, tape, dL_dlogpx, nullptr, o, dx, dp, stats);
+}
+
+extern "C" int b200_ffjord_adjoint_state(b200_ctx* ctx, const b200_model* model, b200_tape* tape,
+                                         const float* dL_dlogpx, const float* dL_dz, const b200_opts* o, float* dx,
+                                         float* dp, b200_stats* stats) {
   int rc = check_common(ctx, model, o, tape ? tape->B : 0);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
-  if (!tape || !dL_dlogpx) return set_err(ctx, B200_ERR_ARG, "null tape/dL_dlogpx");
+  if (!tape || (!dL_dlogpx && !dL_dz)) return set_err(ctx, B200_ERR_ARG, "null tape/dL_dlogpx");
   if (tape->ctx != ctx) return set_err(ctx, B200_ERR_ARG, "tape belongs to another (or a destroyed) context");
   if (tape->fwd_flavor != FL_FWD_FFJORD || !tape->dense)
     return set_err(ctx, B200_ERR_ARG, "tape was not recorded by b200_ffjord_forward with InterpolatingAdjoint");
-  const int B = tape->B, D = tape->D;
+  const int B = tape->B, D = tape->D, NS = tape->NS;
   const MlpDesc& m = tape->m;
   std::vector<void*> temps;
-  const float* g_d;
-  if ((rc = to_device(ctx, dL_dlogpx, (size_t)B, o->ptr_kind, &g_d, temps))) return rc;
+  const float *g_d = nullptr, *gz_d = nullptr;
+  if (dL_dlogpx && (rc = to_device(ctx, dL_dlogpx, (size_t)B, o->ptr_kind, &g_d, temps))) return rc;
+  if (dL_dz && (rc = to_device(ctx, dL_dz, (size_t)B * NS, o->ptr_kind, &gz_d, temps))) { free_temps(ctx, temps); return rc; }
   float* dL_d = nullptr;
-  CU(dalloc(ctx, &dL_d, (size_t)B * (D + 1)));
+  CU(dalloc(ctx, &dL_d, (size_t)B * NS));
   temps.push_back(dL_d);
-  ffjord_seed_kernel<<<(B + 255) / 256, 256, 0, ctx->stream>>>(tape->final_state, g_d, B, D, dL_d);
+  ffjord_seed_kernel<<<(B + 255) / 256, 256, 0, ctx->stream>>>(tape->final_state, g_d, gz_d, B, D, NS, dL_d);
   float *lam = nullptr, *mu = nullptr;
   rc = adjoint_core(ctx, tape, FL_ADJ_FFJORD, dL_d, o, &lam, &mu, stats);
   if (rc >= 0) {
@@ -1085,7 +1102,7 @@ extern "C" int b200_ffjord_adjoint(b200_ctx* ctx, const b200_model* model, b200_
       if (o->ptr_kind == B200_PTR_DEVICE) dx_d = dx; else { e = dalloc(ctx, &dx_d, (size_t)B * D); temps.push_back(dx_d); }
       if (e == cudaSuccess) {
         const long long n = (long long)B * D;
-        extract_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lam, B, D + 1, D, dx_d, 0);
+        extract_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lam, B, NS, D, dx_d, 0);
         if (o->ptr_kind == B200_PTR_HOST) from_device(ctx, dx, dx_d, (size_t)n, B200_PTR_HOST);
       }
     }

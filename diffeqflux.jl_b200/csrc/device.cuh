@@ -189,6 +189,7 @@ struct SolveParams {
   float* mu_out;         // [ppad]
   int exact_trace;       // FFJORD monte_carlo = false: trace of the Jacobian by D unit-vector passes instead of one noise pass
   int rowthread;         // FFJORD forward, all widths <= 64: one thread per trajectory (rhs_ffjord_fwd_rows)
+  int regularize;        // FFJORD regularize = true: state rows D+1, D+2 integrate sum(abs2, m(z)) and ||e^T J||_2 (src/ffjord.jl:131-133)
   int mu_in_norm;        // 1: mu is a state of the adjoint ODE (Interpolating / Backsolve); 0: quadrature (Quadrature / Gauss adjoints)
   // FFJORD
   unsigned long long seed;
@@ -743,7 +744,7 @@ struct Solver {
       else put_input(r, c - D, v);
     } else {  // FL_ADJ_FFJORD
       if (c < D) sm[P.sp.dl_off + r * M.dpad[M.nl] + c] = v;
-      else sm[P.sp.ll_off + r] = v;
+      else sm[P.sp.ll_off + (c - D) * P.TB + r] = v;     // lambda of delta_logp [, of the two regulariser rows]
     }
   }
   __device__ __forceinline__ void put_input(int r, int c, float v) {
@@ -1040,13 +1041,17 @@ struct Solver {
       });
       for (int r = tid; r < P.TB; r += NTHREADS) {
         if (base_row + r < B) {
-          float tr = 0.f;
+          float tr = 0.f, s1 = 0.f, s2 = 0.f;
           float* o = kout + (long long)(base_row + r) * NV;
           for (int d = 0; d < D; ++d) {
-            tr = fmaf(eJ[r * Kp0 + d], e[r * Lp + d], tr);
-            o[d] = mz[r * Lp + d];
+            const float ej = eJ[r * Kp0 + d], m = mz[r * Lp + d];
+            tr = fmaf(ej, e[r * Lp + d], tr);
+            s1 = fmaf(m, m, s1);
+            s2 = fmaf(ej, ej, s2);
+            o[d] = m;
           }
           o[D] = -tr;
+          if (P.regularize) { o[D + 1] = s1; o[D + 2] = sqrtf(s2); }
         }
       }
       sync();
@@ -1118,11 +1123,14 @@ struct Solver {
     const int base_row = tile * TB;
     const int Lp = M.dpad[L];
     float* e = sm + P.sp.dl_off;                       // noise (or the unit vector of the pass), [row][Lp] (fill_noise layout)
-    const int npass = P.exact_trace ? D : 1;           // exact trace: sum_d e_d^T J e_d, one reverse pass per unit vector
+    // exact trace: sum_d e_d^T J e_d, one reverse pass per unit vector; with regularize one more pass with e ~ randn for
+    // ||e^T J|| (src/ffjord.jl:124-125)
+    const int npass = P.exact_trace ? D + (P.regularize ? 1 : 0) : 1;
     float acc[64];
     for (int pass = 0; pass < npass; ++pass) {
     if (pass > 0) sync();                              // every thread has read the previous pass' seed
-    fill_noise(tile, 0u, call, e, Lp, P.exact_trace ? pass : -1);
+    const bool unit_pass = P.exact_trace && pass < D;
+    fill_noise(tile, 0u, call, e, Lp, unit_pass ? pass : -1);
     sync();
     for (int t = tid; t < TB; t += NTHREADS) {
       // ---- forward: h_{l+1} = act(h_l W_l + b_l); hidden h_l kept column-major in the act_off[l] buffer
@@ -1145,13 +1153,19 @@ struct Solver {
             if (n < N) H[n * TB] = act_apply(a, acc[n]);
         } else if (pass == 0 && base_row + t < B) {
           float* o = kout + (long long)(base_row + t) * NV;
+          float s1 = 0.f;
 #pragma unroll
           for (int n = 0; n < 64; ++n)
-            if (n < D) o[n] = act_apply(a, acc[n]);
+            if (n < D) {
+              const float m = act_apply(a, acc[n]);
+              o[n] = m;
+              s1 = fmaf(m, m, s1);
+            }
+          if (P.regularize) o[D + 1] = s1;
         }
       }
       // ---- reverse: eJ = e^T dm/dz; delta_L = e, delta_l = (delta_{l+1} W_l^T) .* act'(h_l), in place in the h buffers
-      float tr = 0.f;
+      float tr = 0.f, s2 = 0.f;
       for (int l = L - 1; l >= 0; --l) {
         const int N = M.dims[l + 1], Kp = M.dpad[l], K = M.dims[l], kq = Kp >> 2;
 #pragma unroll
@@ -1167,12 +1181,16 @@ struct Solver {
         } else {
 #pragma unroll
           for (int k = 0; k < 64; ++k)
-            if (k < D) tr = fmaf(acc[k], e[t * Lp + k], tr);
+            if (k < D) {
+              tr = fmaf(acc[k], e[t * Lp + k], tr);
+              s2 = fmaf(acc[k], acc[k], s2);
+            }
         }
       }
       if (base_row + t < B) {
         float* o = kout + (long long)(base_row + t) * NV + D;
-        *o = pass == 0 ? -tr : *o - tr;
+        if (!P.exact_trace || unit_pass) *o = pass == 0 ? -tr : *o - tr;
+        if (P.regularize && !unit_pass) o[2] = sqrtf(s2);
       }
     }
     }
@@ -1189,24 +1207,46 @@ struct Solver {
     float* hb = sm + P.sp.dl_off;     // hbar_L = lz (already routed)
     float* hdb = sm + P.sp.dl2_off;   // hdbar_L = -ll * e
     const float* ll = sm + P.sp.ll_off;
-    // Exact trace (monte_carlo = false): the RHS is  <lz, m(z)> - ll * sum_d <e_d, J(z) e_d>.  Everything below is linear in
-    // the seed pair (hbar_L, hdbar_L), so D passes with (lz / D, -ll e_d) add up to it; the first pass stores its results
-    // (derivative rows, gradient slabs), the others accumulate.
-    const int npass = P.exact_trace ? D : 1;
-    if (npass > 1) {
-      const float inv = 1.f / (float)npass;
+    // Everything below is linear in the seed pair (hbar_L, hdbar_L) given the tangent direction hdot_0, so the RHS is a sum
+    // of passes; the first emitting pass stores its results (derivative rows, gradient slabs), the others accumulate.
+    //   kind 0 (trace):  Hutchinson: one pass, direction e ~ randn, seeds (lz, -ll e).  Exact trace (monte_carlo = false):
+    //                    <lz, m(z)> - ll * sum_d <e_d, J(z) e_d>  =  D passes with direction e_d, seeds (lz / D, -ll e_d).
+    //   regularize = true adds  l1 * sum(abs2, m(z)) + l2 * ||e^T J||  (l1, l2: cotangents of the two extra state rows):
+    //                    the first term is 2 l1 m(z) more on hbar_L; for the second,
+    //   kind 1:          seeds (e, 0): the z-cotangent of this pass is eJ = e^T J itself (nothing emitted), then
+    //   kind 2:          direction w = l2 eJ / ||eJ|| held constant, seeds (0, e):  d/d(z,p) <e, J w>.
+    const int nT = P.exact_trace ? D : 1;
+    const int npass = nT + (P.regularize ? 2 : 0);
+    if (nT > 1) {
+      const float inv = 1.f / (float)nT;
       for (int e = tid; e < P.TB * Lp; e += NTHREADS) hb[e] *= inv;
       sync();
     }
+    bool emitted = false;
     for (int pass = 0; pass < npass; ++pass) {
-    const bool acc_pass = pass > 0;
-    const bool acc_store_p = acc_store || acc_pass;
-    // hdot_0 = e
-    fill_noise(tile, 1u, call, sm + P.sp.hd_off[0], M.dpad[0], P.exact_trace ? pass : -1);
-    sync();
-    for (int e = tid; e < P.TB * Lp; e += NTHREADS) {
-      const int r = e / Lp, c = e - r * Lp;
-      hdb[e] = (c < D) ? -ll[r] * sm[P.sp.hd_off[0] + r * M.dpad[0] + c] : 0.f;
+    const int kind = pass < nT ? 0 : (pass == nT ? 1 : 2);
+    const bool emit = kind != 1;
+    const bool acc_pass = emitted;
+    const bool acc_store_p = acc_store || emitted;
+    float* dir = sm + P.sp.hd_off[0];                    // hdot_0
+    if (kind == 0) {
+      fill_noise(tile, 1u, call, dir, M.dpad[0], P.exact_trace ? pass : -1);
+      sync();
+      for (int e = tid; e < P.TB * Lp; e += NTHREADS) {
+        const int r = e / Lp, c = e - r * Lp;
+        hdb[e] = (c < D) ? -ll[r] * dir[r * M.dpad[0] + c] : 0.f;
+      }
+    } else if (kind == 1) {
+      fill_noise(tile, 1u, call, dir, M.dpad[0]);        // (any finite direction: hdbar = 0 makes the pass first order)
+      for (int e = tid; e < P.TB * Lp; e += NTHREADS) { hb[e] = 0.f; hdb[e] = 0.f; }
+      sync();
+      fill_noise(tile, 1u, call, hb, Lp);
+      sync();
+    } else {
+      for (int e = tid; e < P.TB * Lp; e += NTHREADS) { hb[e] = 0.f; hdb[e] = 0.f; }
+      sync();
+      fill_noise(tile, 1u, call, hdb, Lp);
+      sync();
     }
     // forward of (h, hdot); hidden layers store h_l, q_l, hdot_l
     for (int l = 0; l < L - 1; ++l) {
@@ -1247,14 +1287,40 @@ struct Solver {
                 });
       sync();
     }
+    if (P.regularize && pass == 0) {
+      // hbar_L += 2 l1 m(z) (/ D in the exact-trace split): m(z) = h_{L-1} W_{L-1} + b_{L-1}, the one layer the doubled
+      // forward above does not evaluate
+      const int Kp = M.dpad[L - 1], Np = M.dpad[L];
+      const float* bias = P.wp + M.b_off[L - 1];
+      const float* l1 = ll + P.TB;
+      const float sc = 2.f / (float)nT;
+      tile_gemm(sm + P.sp.act_off[L - 1], Kp, P.wp + M.w_off[L - 1], Np, P.TB, Kp, Np,
+                [&](int row0, int col0, float (&acc)[8][4]) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0));
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float4* hp = reinterpret_cast<float4*>(hb + (row0 + i) * Np + col0);
+                    const float w = sc * l1[row0 + i];
+                    float4 v = *hp;
+                    if (col0 + 0 < D) v.x = fmaf(w, acc[i][0] + b.x, v.x);
+                    if (col0 + 1 < D) v.y = fmaf(w, acc[i][1] + b.y, v.y);
+                    if (col0 + 2 < D) v.z = fmaf(w, acc[i][2] + b.z, v.z);
+                    if (col0 + 3 < D) v.w = fmaf(w, acc[i][3] + b.w, v.w);
+                    *hp = v;
+                  }
+                });
+      sync();
+    }
     // reverse: (prebar_l, qbar_l) live in (X, Y); last layer is identity so they are the seeds
     const float* X = hb;
     const float* Y = hdb;
     for (int l = L; l >= 1; --l) {
       const int li = l - 1;
       const int Np = M.dpad[l], Kp = M.dpad[li];
-      layer_wgrad(li, sm + P.sp.act_off[li], X, sm + P.sp.hd_off[li], Y, so, acc_store_p);
-      sync();
+      if (emit) {
+        layer_wgrad(li, sm + P.sp.act_off[li], X, sm + P.sp.hd_off[li], Y, so, acc_store_p);
+        sync();
+      }
       const float* WT = P.wtp + M.wt_off[li];
       if (li >= 1) {
         const int a = M.act[li - 1], Kd = M.dims[li];
@@ -1305,7 +1371,9 @@ struct Solver {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = row0 + i;
-            if (base_row + row < B) {
+            if (!emit) {                                 // kind 1: eJ = e^T J into the direction buffer of the next pass
+              *reinterpret_cast<float4*>(dir + row * Kp + col0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            } else if (base_row + row < B) {
               float* o = kout + (long long)(base_row + row) * NV + col0;
               if (col0 + 0 < D) o[0] = (acc_pass ? o[0] : 0.f) - acc[i][0];
               if (col0 + 1 < D) o[1] = (acc_pass ? o[1] : 0.f) - acc[i][1];
@@ -1314,11 +1382,27 @@ struct Solver {
             }
           }
         });
-        for (int r = tid; r < P.TB; r += NTHREADS)
-          if (base_row + r < B) kout[(long long)(base_row + r) * NV + D] = 0.f;
+        if (emit) {
+          for (int r = tid; r < P.TB; r += NTHREADS)
+            if (base_row + r < B)
+              for (int c = D; c < NV; ++c) kout[(long long)(base_row + r) * NV + c] = 0.f;
+        }
         sync();
+        if (!emit) {
+          // w = l2 * eJ / ||eJ||_2 per trajectory (0 where the norm vanishes: the reference's sqrt has no derivative there)
+          const float* l2 = ll + 2 * P.TB;
+          for (int r = tid; r < P.TB; r += NTHREADS) {
+            float* w = dir + r * Kp;
+            float s2 = 0.f;
+            for (int d = 0; d < D; ++d) s2 = fmaf(w[d], w[d], s2);
+            const float nrm = sqrtf(s2);
+            for (int d = 0; d < Kp; ++d) w[d] = (d < D && nrm > 0.f) ? (l2[r] * w[d]) / nrm : 0.f;
+          }
+          sync();
+        }
       }
     }
+    if (emit) emitted = true;
     }   // pass
   }
 

@@ -10,7 +10,7 @@
 #     Zygote.gradient(sum ∘ first ∘ node, u0, ps, st)
 # keep working, with ONE ccall per solve and ONE ccall per pullback.  Every layer has its ChainRules `rrule`
 # (Zygote never differentiates through a ccall).  Unsupported configurations (non-Tsit5 solver, non-Dense model,
-# Float64, other sensealgs, FFJORD's regularize / exact-trace branches) throw: there is no CPU fallback.
+# Float64, other sensealgs, FFJORD with a basedist or AutoForwardDiff) throw: there is no CPU fallback.
 module B200DiffEqFlux
 
 using ChainRulesCore, Lux, LuxCore, ComponentArrays, SciMLBase, Libdl, Random
@@ -40,7 +40,7 @@ Base.@kwdef mutable struct B200Opts
     save_everystep::Cint = 0
     path::Cint = 0              # 0 auto, 1 FFMA only, 2 require tcgen05
     ffjord_exact_trace::Cint = 0    # FFJORD monte_carlo = false
-    reserved::NTuple{1, Cint} = (0,)
+    ffjord_regularize::Cint = 0     # FFJORD regularize = true (two more state rows)
 end
 
 mutable struct B200Stats
@@ -229,7 +229,7 @@ function (dm::DimMover)(x::Array{Float32}, ps, st)
     return reshape(out, Int.(od[1:nd[]])...), st
 end
 
-# ---- FFJORD (src/ffjord.jl:52-245), monte_carlo = true / regularize = false branch -------------------
+# ---- FFJORD (src/ffjord.jl:52-245): monte_carlo / regularize flags of `st` as in the reference -----------
 struct FFJORD{M, T, A, K} <: LuxCore.AbstractLuxWrapperLayer{:model}
     model::M
     tspan::T
@@ -242,13 +242,12 @@ FFJORD(model, tspan, input_dims, args...; ad = nothing, basedist = nothing, kwar
 LuxCore.initialstates(rng, n::FFJORD) = (; model = LuxCore.initialstates(rng, n.model), regularize = false, monte_carlo = true)
 
 function ffjord_forward(n::FFJORD, x::AbstractMatrix{Float32}, pv, st, tspan; want_tape::Bool, seed = rand(UInt64))
-    st.regularize && error("B200 path: regularize = true is not supported")
     B = size(x, 2)
     logpx = Vector{Float32}(undef, B)
-    z = Matrix{Float32}(undef, size(x, 1) + 1, B)
+    z = Matrix{Float32}(undef, size(x, 1) + (st.regularize ? 3 : 1), B)
     o = B200Opts(; abstol = get(n.kwargs, :abstol, 1.0f-6), reltol = get(n.kwargs, :reltol, 1.0f-3),
                  sensealg = want_tape ? 0 : -1, seed,             # InterpolatingAdjoint is hard-wired at src/ffjord.jl:143
-                 ffjord_exact_trace = st.monte_carlo ? 0 : 1)
+                 ffjord_exact_trace = st.monte_carlo ? 0 : 1, ffjord_regularize = st.regularize ? 1 : 0)
     tape = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall(sym(:b200_ffjord_forward), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cfloat, Cfloat, Ref{B200Opts}, Ptr{Cfloat}, Ptr{Cfloat},
@@ -257,30 +256,47 @@ function ffjord_forward(n::FFJORD, x::AbstractMatrix{Float32}, pv, st, tspan; wa
                 want_tape ? tape : C_NULL))
     return logpx, z, (want_tape ? Tape(tape[]) : nothing), o
 end
+# (delta_logp, lambda_1, lambda_2) out of the end state, the selections of src/ffjord.jl:161-169 verbatim
+function ffjord_outputs(z, regularize::Bool)
+    L = size(z, 1)
+    i1 = L - (regularize ? 2 : 0)
+    Δlogp = z[i1:i1, :]
+    regularize || return Δlogp, Δlogp, Δlogp
+    return Δlogp, z[:, (L - 1):(L - 1)], z[:, L:L]
+end
 function (n::FFJORD)(x::AbstractMatrix{Float32}, ps, st)
     logpx, z, _, _ = ffjord_forward(n, x, collect(ps), st, n.tspan; want_tape = false)
-    Δlogp = z[end:end, :]
-    return (reshape(logpx, 1, :), Δlogp, Δlogp), st
+    _, λ1, λ2 = ffjord_outputs(z, st.regularize)
+    return (reshape(logpx, 1, :), λ1, λ2), st
 end
 function ChainRulesCore.rrule(n::FFJORD, x::AbstractMatrix{Float32}, ps, st)
     pv = collect(ps)
     logpx, z, tape, o = ffjord_forward(n, x, pv, st, n.tspan; want_tape = true)
-    Δlogp = z[end:end, :]
+    _, λ1, λ2 = ffjord_outputs(z, st.regularize)
     function ffjord_pullback(Δ)
-        g = Float32.(vec(first(first(Δ))))                         # cotangent of logpx (the regulariser outputs carry none here)
+        Δout = first(Δ)
+        Δ1 = Δout[1]
+        g = Δ1 isa AbstractArray ? Float32.(vec(Δ1)) : zeros(Float32, size(x, 2))         # cotangent of logpx
+        gz = zeros(Float32, size(z))                                                        # cotangent of the end state
+        if st.regularize
+            L = size(z, 1)
+            Δout[2] isa AbstractArray && (gz[:, L - 1] .+= vec(Δout[2]))
+            Δout[3] isa AbstractArray && (gz[:, L] .+= vec(Δout[3]))
+        end
         dx = similar(x); dp = similar(pv)
-        check(ccall(sym(:b200_ffjord_adjoint), Cint,
-                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cfloat}, Ref{B200Opts}, Ptr{Cfloat}, Ptr{Cfloat}, Ref{B200Stats}),
-                    ctx(), model_handle(n.model), tape.h, g, o, dx, dp, B200Stats()))
+        check(ccall(sym(:b200_ffjord_adjoint_state), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cfloat}, Ptr{Cfloat}, Ref{B200Opts}, Ptr{Cfloat}, Ptr{Cfloat},
+                     Ref{B200Stats}),
+                    ctx(), model_handle(n.model), tape.h, g, gz, o, dx, dp, B200Stats()))
         return NoTangent(), dx, ComponentArray(dp, getaxes(ps)), NoTangent()
     end
-    return ((reshape(logpx, 1, :), Δlogp, Δlogp), st), ffjord_pullback
+    return ((reshape(logpx, 1, :), λ1, λ2), st), ffjord_pullback
 end
 # `__backward_ffjord` (src/ffjord.jl:183-214): samples = reverse-time flow of z ~ N(0, I)
 function backward_ffjord(n::FFJORD, n_samples::Int, ps, st, rng = Random.default_rng())
     zs = randn(rng, Float32, n.input_dims..., n_samples)
     _, z, _, _ = ffjord_forward(n, reshape(zs, :, n_samples), collect(ps), st, reverse(n.tspan); want_tape = false)
-    return z[1:(end - 1), :]
+    return z[1:(end - (st.regularize ? 3 : 1)), :]
 end
 struct FFJORDDistribution{F <: FFJORD, P, S}
     model::F

@@ -548,22 +548,28 @@ class AugmentedNDELayer:
 # --------------------------------------------------------------------------------------- FFJORD
 if torch is not None:
     class _FfjordFn(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, x, p, layer, seed, holder):
-            seed, exact = seed
-            fw = layer._forward(x, p, seed, want_tape=True, exact=exact)
-            holder.update(fw)
-            ctx.layer, ctx.fw, ctx.owner = layer, fw, _TapeOwner(fw["tape"])
-            out = fw["logpx"]
-            return out if _is_torch(out) else torch.from_numpy(out)
+        """(logpx, end state) of the FFJORD solve; both outputs carry gradients (lambda_1 / lambda_2 of a regularize = true
+        layer are slices of the end state)."""
 
         @staticmethod
-        def backward(ctx, g):
+        def forward(ctx, x, p, layer, seed, holder):
+            seed, exact, regularize = seed
+            fw = layer._forward(x, p, seed, want_tape=True, exact=exact, regularize=regularize)
+            holder.update(fw)
+            ctx.layer, ctx.fw, ctx.owner = layer, fw, _TapeOwner(fw["tape"])
+            out, z = fw["logpx"], fw["z"]
+            if not _is_torch(out):
+                out, z = torch.from_numpy(out), torch.from_numpy(z)
+            return out, z.clone()
+
+        @staticmethod
+        def backward(ctx, g, gz):
             fw = ctx.fw
             g = g.contiguous().reshape(-1)
+            gz = gz.contiguous()
             if not fw["on_dev"]:
-                g = g.cpu().numpy()
-            dx, dp = ctx.layer._adjoint(fw, g)
+                g, gz = g.cpu().numpy(), gz.cpu().numpy()
+            dx, dp = ctx.layer._adjoint(fw, g, gz)
             if not _is_torch(dx):
                 dx, dp = torch.from_numpy(dx), torch.from_numpy(dp)
             return dx, dp, None, None, None
@@ -571,9 +577,9 @@ if torch is not None:
 
 class FFJORD:
     """`FFJORD(model, tspan, input_dims, args...; ad, basedist, kwargs...)` (src/ffjord.jl:52-73),
-    called as `(x, ps, st) -> ((logpx, l1, l2), st)` (src/ffjord.jl:138-178).  Only the branch
-    regularize=false, monte_carlo=true, ad in (nothing, AutoZygote), basedist=nothing is on the B200
-    path; the others raise."""
+    called as `(x, ps, st) -> ((logpx, l1, l2), st)` (src/ffjord.jl:138-178).  `st["monte_carlo"]` picks the Hutchinson
+    estimator or the exact trace, `st["regularize"]` adds the two regulariser rows to the state (src/ffjord.jl:61-66);
+    ad in (nothing, AutoZygote) and basedist = nothing; anything else raises."""
 
     def __init__(self, model, tspan, input_dims, *args, ad=None, basedist=None, **kwargs):
         if not isinstance(model, Chain):
@@ -595,7 +601,7 @@ class FFJORD:
         return {"model": {}, "regularize": False, "monte_carlo": True,
                 "seed": int(rng.integers(0, 2**62)) if hasattr(rng, "integers") else 0, "calls": 0}
 
-    def _forward(self, x, p, seed, want_tape, exact=False):
+    def _forward(self, x, p, seed, want_tape, exact=False, regularize=False):
         xb, pb = _Buf(x), _Buf(p)
         shape = tuple(xb.t.shape) if _is_torch(x) else xb.a.shape
         if len(shape) != 2 or shape[1] != self.model.dims[0]:
@@ -609,73 +615,92 @@ class FFJORD:
         o.seed = int(seed) & (2**64 - 1)
         o.noise_per_call = int(self.kwargs.get("noise_per_call", 1))
         o.ffjord_exact_trace = 1 if exact else 0        # monte_carlo = false (src/ffjord.jl:120-123)
+        o.ffjord_regularize = 1 if regularize else 0    # src/ffjord.jl:131-133,149-153
         o.b_offset = _dist_state["rank"] * B            # global trajectory index of this shard (noise stream)
         if want_tape:
             o.sensealg = N.SENSE_INTERPOLATING      # hard-wired at src/ffjord.jl:143
         st = N.Stats()
         tape = C.c_void_p()
+        NS = D + (3 if regularize else 1)
         logpx = _alloc((B,), x, on_dev, dev)
-        z = _alloc((B, D + 1), x, on_dev, dev)
+        z = _alloc((B, NS), x, on_dev, dev)
         t0, t1 = self.tspan
         rc = ctx.check(N.lib().b200_ffjord_forward(ctx._h, mh, pb.ptr, xb.ptr, B, float(t0), float(t1), C.byref(o),
                                                    _ptr(logpx), _ptr(z), C.byref(st),
                                                    C.byref(tape) if want_tape else None))
         stats = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile, st.engine)
-        return dict(ctx=ctx, mh=mh, tape=tape, logpx=logpx, z=z, rc=rc, stats=stats, B=B, D=D, on_dev=on_dev,
-                    dev=dev, opts=o)
+        return dict(ctx=ctx, mh=mh, tape=tape, logpx=logpx, z=z, rc=rc, stats=stats, B=B, D=D, NS=NS, on_dev=on_dev,
+                    dev=dev, opts=o, regularize=bool(regularize))
 
-    def _adjoint(self, fw, g):
+    def _adjoint(self, fw, g, gz=None):
+        """g: cotangent of logpx [B] (or None); gz: cotangent of the end state [B][NS] (or None)."""
         ctx, o = fw["ctx"], fw["opts"]
-        gb = _Buf(g)
+        gb = _Buf(g) if g is not None else None
+        gzb = _Buf(gz) if gz is not None else None
         dx = _alloc((fw["B"], fw["D"]), None, fw["on_dev"], fw["dev"])
         dp = _alloc((self.model.nparams,), None, fw["on_dev"], fw["dev"])
         st = N.Stats()
-        rc = ctx.check(N.lib().b200_ffjord_adjoint(ctx._h, fw["mh"], fw["tape"], gb.ptr, C.byref(o), _ptr(dx),
-                                                   _ptr(dp), C.byref(st)))
+        rc = ctx.check(N.lib().b200_ffjord_adjoint_state(ctx._h, fw["mh"], fw["tape"], gb.ptr if gb else None,
+                                                         gzb.ptr if gzb else None, C.byref(o), _ptr(dx), _ptr(dp), C.byref(st)))
         fw["adjoint_stats"] = SolveStats(st.nf, st.naccept, st.nreject, st.kernel_ms, st.tie_dist, st.grid, st.tile, st.engine)
         fw["adjoint_rc"] = rc
         return dx, dp
 
+    @staticmethod
+    def _lambdas(z, D, regularize):
+        """(delta_logp, lambda_1, lambda_2) out of the end state z [B][NS], literally as src/ffjord.jl:161-169 takes them:
+        delta_logp = row D of every trajectory; with regularize the reference selects along the LAST (batch) axis,
+        `selectdim(pred, N, (L-1):(L-1))` and `selectdim(pred, N, L:L)` with L = D + 3 -- the full state of trajectories
+        L-1 and L (1-based), Julia shape (L, 1) = C-order (1, L) here.  (The regulariser integrals themselves are
+        z[:, D+1] and z[:, D+2].)"""
+        dlp = z[:, D].reshape(1, -1)
+        if not regularize:
+            return dlp, dlp, dlp
+        L = D + 3
+        if z.shape[0] < L:
+            raise IndexError(f"BoundsError: regularize = true reads trajectories {L - 1} and {L} of a batch of {z.shape[0]}")
+        return dlp, z[L - 2:L - 1, :], z[L - 1:L, :]
+
     def __call__(self, x, ps, st):
-        if st.get("regularize", False):
-            raise UnsupportedError("regularize = true is outside the B200 path")
+        regularize = bool(st.get("regularize", False))
         exact = not st.get("monte_carlo", True)
         seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
         needs_grad = _is_torch(x) and _is_torch(ps) and torch.is_grad_enabled() and (x.requires_grad or ps.requires_grad)
         if needs_grad:
             self.last = {}
-            logpx = _FfjordFn.apply(x, ps, self, (seed, exact), self.last)
+            logpx, z = _FfjordFn.apply(x, ps, self, (seed, exact, regularize), self.last)
         else:
-            self.last = self._forward(x, ps, seed, want_tape=False, exact=exact)
-            logpx = self.last["logpx"]
-        logpx = logpx.reshape(1, -1) if not _is_torch(logpx) else logpx.reshape(1, -1)
-        z = self.last["z"]
-        delta_logp = z[:, -1].reshape(1, -1)
+            self.last = self._forward(x, ps, seed, want_tape=False, exact=exact, regularize=regularize)
+            logpx, z = self.last["logpx"], self.last["z"]
+        logpx = logpx.reshape(1, -1)
+        _, l1, l2 = self._lambdas(z, self.model.dims[0], regularize)
         st2 = dict(st)
         st2["calls"] = int(st.get("calls", 0)) + 1
-        return (logpx, delta_logp, delta_logp), st2
+        return (logpx, l1, l2), st2
 
     def pullback(self, x, ps, st):
-        if st.get("regularize", False):
-            raise UnsupportedError("regularize = true is outside the B200 path")
+        """-> (logpx, back);  back(g_logpx, g_z = None) -> (dx, dp), g_z the cotangent of the end state `self.last["z"]`
+        ([B][D+1], or [B][D+3] with regularize: columns D+1, D+2 are the regulariser integrals)."""
         seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
-        fw = self._forward(x, ps, seed, want_tape=True, exact=not st.get("monte_carlo", True))
+        fw = self._forward(x, ps, seed, want_tape=True, exact=not st.get("monte_carlo", True),
+                           regularize=bool(st.get("regularize", False)))
         owner = _TapeOwner(fw["tape"])
         self.last = fw
 
-        def back(g):
+        def back(g, gz=None):
             _ = owner
-            return self._adjoint(fw, np.asarray(g, np.float32).reshape(-1) if not _is_torch(g) else g.reshape(-1))
+            if g is not None:
+                g = np.asarray(g, np.float32).reshape(-1) if not _is_torch(g) else g.reshape(-1)
+            if gz is not None:
+                gz = np.ascontiguousarray(gz, np.float32) if not _is_torch(gz) else gz.contiguous()
+            return self._adjoint(fw, g, gz)
 
         return fw["logpx"], back
-
 
     def backward(self, n_samples: int, ps, st, rng=None, z=None):
         """`__backward_ffjord(T, n, n_samples, ps, st, rng)` (src/ffjord.jl:183-214): draw z ~ N(0, I) (or take `z`),
         integrate the same augmented RHS over reverse(tspan) and return the first D rows of the end state -- samples of
         the learned density.  One b200_ffjord_forward call with the time span reversed."""
-        if st.get("regularize", False):
-            raise UnsupportedError("regularize = true is outside the B200 path")
         D = self.model.dims[0]
         if z is None:
             rng = np.random.default_rng() if rng is None else rng
@@ -684,7 +709,8 @@ class FFJORD:
                 z = torch.from_numpy(z).to(ps.device)
         seed = (int(st.get("seed", 0)) + 0x9E3779B97F4A7C15 * int(st.get("calls", 0))) & (2**64 - 1)
         rev = FFJORD(self.model, (self.tspan[1], self.tspan[0]), self.input_dims, *self.args, **self.kwargs)
-        fw = rev._forward(z, ps, seed, want_tape=False, exact=not st.get("monte_carlo", True))
+        fw = rev._forward(z, ps, seed, want_tape=False, exact=not st.get("monte_carlo", True),
+                          regularize=bool(st.get("regularize", False)))
         self.last = fw
         return fw["z"][:, :D]
 

@@ -90,7 +90,8 @@ typedef struct b200_opts {
                             3xTF32 tensor-core engine (error if the model shape is not eligible) */
   int ffjord_exact_trace;/* FFJORD: 1 = monte_carlo = false (src/ffjord.jl:120-123): the trace of the Jacobian is exact (D
                             unit-vector passes per RHS call instead of one Hutchinson noise pass); networks with widths <= 64 */
-  int reserved[1];
+  int ffjord_regularize; /* FFJORD: 1 = regularize = true (src/ffjord.jl:131-133,149-153): the state carries two more rows,
+                          * d/dt = [sum(abs2, m(z)); ||e^T J||_2]; end state / cotangents are [B][D+3] */
 } b200_opts;
 
 typedef struct b200_stats {
@@ -162,7 +163,8 @@ void b200_tape_free(b200_tape* tape);
 /* Replaces `__forward_ffjord` (src/ffjord.jl:140-178) with regularize=false, monte_carlo=true,
  * basedist=nothing: augment one delta_logp row, solve to t1 with the Hutchinson RHS `__ffjord`
  * (src/ffjord.jl:81-136), logpx = logpz - delta_logp.
- *   x [B][D]; logpx [B]; z_out (nullable) [B][D+1] end state. */
+ *   x [B][D]; logpx [B]; z_out (nullable) [B][D+1] end state ([B][D+3] with opts->ffjord_regularize: the reference's
+ *   lambda_1 / lambda_2 outputs, src/ffjord.jl:164-166, are slices of it the caller takes). */
 int b200_ffjord_forward(b200_ctx* ctx, const b200_model* model, const float* p, const float* x,
                         int B, float t0, float t1, const b200_opts* opts, float* logpx,
                         float* z_out, b200_stats* stats, b200_tape** tape);
@@ -171,6 +173,12 @@ int b200_ffjord_forward(b200_ctx* ctx, const b200_model* model, const float* p, 
 int b200_ffjord_adjoint(b200_ctx* ctx, const b200_model* model, b200_tape* tape,
                         const float* dL_dlogpx, const b200_opts* opts, float* dx, float* dp,
                         b200_stats* stats);
+/* Same pullback with a cotangent on the whole end state as well (what Zygote hands the solve when the loss also uses
+ * lambda_1 / lambda_2 of a regularize = true layer, src/ffjord.jl:164-166,177):
+ *   dL_dlogpx [B] (nullable); dL_dz [B][NS] (nullable) cotangent of z_out, NS = D+1 or D+3; at least one is given. */
+int b200_ffjord_adjoint_state(b200_ctx* ctx, const b200_model* model, b200_tape* tape,
+                              const float* dL_dlogpx, const float* dL_dz, const b200_opts* opts, float* dx,
+                              float* dp, b200_stats* stats);
 
 /* ---- multiple shooting ----------------------------------------------------------------------- */
 /* `group_ranges(datasize, groupsize)` (src/multiple_shooting.jl:231-239): writes 0-based

@@ -48,12 +48,14 @@ class NodeProblem:
 
 class FfjordProblem:
     """state rows [z (D); delta_logp (1)], RHS = [m(z); -e^T J e] with fresh e per RHS call
-    (/root/reference/src/ffjord.jl:85-92,105-115,134)."""
+    (/root/reference/src/ffjord.jl:85-92,105-115,134).
+    regularize = true (/root/reference/src/ffjord.jl:131-133,149-153): two more rows, d/dt = [sum(abs2, m(z)); ||e^T J||_2]."""
 
-    def __init__(self, mlp: MLP, seed: int, b_offset: int = 0, monte_carlo: bool = True):
+    def __init__(self, mlp: MLP, seed: int, b_offset: int = 0, monte_carlo: bool = True, regularize: bool = False):
         self.mlp = mlp
         self.D = mlp.dims[0]
-        self.ns = self.D + 1
+        self.regularize = regularize
+        self.ns = self.D + (3 if regularize else 1)
         self.seed = seed
         self.b_offset = b_offset
         # monte_carlo = false (/root/reference/src/ffjord.jl:120-123): the trace of the batched Jacobian itself, here as
@@ -69,42 +71,73 @@ class FfjordProblem:
             e[:, d] = 1
             yield e
 
+    def _reg_rows(self, mz, eJ):
+        """rows D+1, D+2 of the RHS: sum(abs2, mz) and sqrt(sum(abs2, eJ)) per trajectory (src/ffjord.jl:78-79,132)."""
+        r1 = np.sum(mz * mz, axis=1, dtype=self.mlp.dtype)
+        r2 = np.sqrt(np.sum(eJ * eJ, axis=1, dtype=self.mlp.dtype)).astype(self.mlp.dtype)
+        return [r1[:, None], r2[:, None]]
+
     def f(self, p, y, call, stream):
         z = np.ascontiguousarray(y[:, :self.D])
         mz, cache = self.mlp.forward(p, z)
         if not self.monte_carlo:
-            tr = np.zeros(z.shape[0], np.float32)
+            tr = np.zeros(z.shape[0], self.mlp.dtype)
             for e in self.units(z.shape[0]):
                 eJ, _ = self.mlp.vjp(cache, e, want_dp=False)
-                tr = (tr + np.sum(eJ * e, axis=1, dtype=np.float32)).astype(np.float32)
-            return np.concatenate([mz, -tr[:, None]], axis=1).astype(np.float32), None
+                tr = (tr + np.sum(eJ * e, axis=1, dtype=self.mlp.dtype)).astype(self.mlp.dtype)
+            rows = [mz, -tr[:, None]]
+            if self.regularize:                           # e ~ randn, eJ = e^T J (src/ffjord.jl:124-125)
+                eJ, _ = self.mlp.vjp(cache, self.noise(z.shape[0], call, stream), want_dp=False)
+                rows += self._reg_rows(mz, eJ)
+            return np.concatenate(rows, axis=1).astype(self.mlp.dtype), None
         e = self.noise(z.shape[0], call, stream)
         eJ, _ = self.mlp.vjp(cache, e, want_dp=False)
-        tr = np.sum(eJ * e, axis=1, dtype=np.float32)
-        out = np.concatenate([mz, -tr[:, None]], axis=1).astype(np.float32)
-        return out, None
+        tr = np.sum(eJ * e, axis=1, dtype=self.mlp.dtype)
+        rows = [mz, -tr[:, None]]
+        if self.regularize:
+            rows += self._reg_rows(mz, eJ)
+        return np.concatenate(rows, axis=1).astype(self.mlp.dtype), None
 
     def vjp(self, p, y, lam, call, stream):
+        """(f(y), lam^T df/dy, lam^T df/dp) of  <lz, m> - ll * tr  [+ l1 * sum(m^2) + l2 * ||e^T J||].
+        Everything is a sum of second-order reverse passes through the doubled (h, hdot) network, each linear in its seed
+        pair (hbar_L, hdbar_L) with tangent direction hdot_0:
+          trace (Hutchinson):  direction e,    seeds (lz [+ 2 l1 m(z)], -ll e)
+          trace (exact):       direction e_d,  seeds ((lz [+ 2 l1 m(z)]) / D, -ll e_d) for every unit vector
+          ||e^T J||:           direction w = l2 * eJ / ||eJ|| (held constant), seeds (0, e):  d/d(z,p) <e, J w>"""
         z = np.ascontiguousarray(y[:, :self.D])
         lz = np.ascontiguousarray(lam[:, :self.D])
         ll = lam[:, self.D:self.D + 1]
+        B = z.shape[0]
+        zeros_tail = np.zeros((B, self.ns - self.D), np.float32)
+        out, _ = self.f(p, y, call, stream)
+        if self.regularize:
+            l1 = lam[:, self.D + 1:self.D + 2]
+            l2 = lam[:, self.D + 2:self.D + 3]
+            lz = (lz + np.float32(2) * l1 * out[:, :self.D]).astype(np.float32)
         if not self.monte_carlo:
-            out, _ = self.f(p, y, call, stream)
             zbar = np.zeros_like(z)
             pbar = np.zeros(p.size, np.float32)
-            for e in self.units(z.shape[0]):          # linear in the seeds: (lz / D, -ll e_d) per unit vector
+            for e in self.units(B):          # linear in the seeds: (lz / D, -ll e_d) per unit vector
                 _, _, cache = self.mlp.jvp_forward(p, z, e)
                 zb, pb = self.mlp.second_order_vjp(cache, (lz / np.float32(self.D)).astype(np.float32), (-ll * e).astype(np.float32))
                 zbar = (zbar + zb).astype(np.float32)
                 pbar = (pbar + pb).astype(np.float32)
-            ybar = np.concatenate([zbar, np.zeros_like(ll)], axis=1).astype(np.float32)
-            return out, ybar, pbar
-        e = self.noise(z.shape[0], call, stream)
-        hL, hdL, cache = self.mlp.jvp_forward(p, z, e)
-        tr = np.sum(hdL * e, axis=1, dtype=np.float32)
-        out = np.concatenate([hL, -tr[:, None]], axis=1).astype(np.float32)
-        zbar, pbar = self.mlp.second_order_vjp(cache, lz, (-ll * e).astype(np.float32))
-        ybar = np.concatenate([zbar, np.zeros_like(ll)], axis=1).astype(np.float32)
+        else:
+            e = self.noise(B, call, stream)
+            hL, hdL, cache = self.mlp.jvp_forward(p, z, e)
+            zbar, pbar = self.mlp.second_order_vjp(cache, lz, (-ll * e).astype(np.float32))
+        if self.regularize:
+            e = self.noise(B, call, stream)
+            _, cache1 = self.mlp.forward(p, z)
+            eJ, _ = self.mlp.vjp(cache1, e, want_dp=False)
+            nrm = np.sqrt(np.sum(eJ * eJ, axis=1, dtype=np.float32)).astype(np.float32)[:, None]
+            w = np.where(nrm > 0, l2 * eJ / np.where(nrm > 0, nrm, np.float32(1)), np.float32(0)).astype(np.float32)
+            _, _, cache = self.mlp.jvp_forward(p, z, w)
+            zb, pb = self.mlp.second_order_vjp(cache, np.zeros_like(e), e)
+            zbar = (zbar + zb).astype(np.float32)
+            pbar = (pbar + pb).astype(np.float32)
+        ybar = np.concatenate([zbar, zeros_tail], axis=1).astype(np.float32)
         return out, ybar, pbar
 
 

@@ -63,7 +63,13 @@ def test_unsupported_configurations_raise():
     st = ff.initialstates(np.random.default_rng(0))
     assert st["regularize"] is False and st["monte_carlo"] is True     # src/ffjord.jl:61-66
     with pytest.raises(dfx.UnsupportedError):
-        ff(np.zeros((4, 2), np.float32), np.zeros(chain.nparams, np.float32), {**st, "regularize": True})
+        dfx.FFJORD(chain, (0.0, 1.0), (2,), dfx.Tsit5(), ad="AutoForwardDiff")
+    # lambda_1 / lambda_2 of a regularize = true layer are taken out of the end state exactly as src/ffjord.jl:164-166 does
+    z = np.arange(7 * 5, dtype=np.float32).reshape(7, 5)               # B = 7 trajectories, D = 2 -> L = 5 rows each
+    dlp, l1, l2 = ff._lambdas(z, 2, True)
+    assert np.array_equal(dlp, z[:, 2].reshape(1, -1)) and np.array_equal(l1, z[3:4]) and np.array_equal(l2, z[4:5])
+    with pytest.raises(IndexError):
+        ff._lambdas(z[:4], 2, True)
 
 
 def test_setup_and_parameter_layout():

@@ -364,3 +364,54 @@ def test_ffjord_exact_trace_restatement():
         fd = (phi(zp) - phi(zm)) / (2 * h)
         assert abs(fd - ybar[b, k]) <= 2e-2 * max(1.0, abs(fd)), (fd, ybar[b, k])
     assert pbar.shape == p.shape and np.abs(pbar).max() > 0
+
+
+@pytest.mark.parametrize("monte_carlo", [True, False])
+def test_ffjord_regularize_restatement(monte_carlo):
+    """regularize = true (src/ffjord.jl:131-133): rows D+1, D+2 of the RHS are sum(abs2, m(z)) and ||e^T J||_2 (checked
+    against an fp64 finite-difference Jacobian), and the adjoint RHS is the derivative of <lam, f> with all four cotangent
+    blocks live (finite differences in z and in p, noise held fixed)."""
+    rng = np.random.default_rng(19)
+    dims, acts = [3, 8, 3], [ACT_TANH, ACT_ID]
+    mlp, mlp64 = MLP(dims, acts), MLP(dims, acts, dtype=np.float64)
+    p = mlp.init(rng, scale=1.5)
+    B = 5
+    z = rng.standard_normal((B, 3)).astype(np.float32)
+    prob = node.FfjordProblem(mlp, seed=1, monte_carlo=monte_carlo, regularize=True)
+    assert prob.ns == 6
+    y = np.concatenate([z, np.zeros((B, 3), np.float32)], 1)
+    out, _ = prob.f(p, y, 4, 0)
+    assert out.shape == (B, 6)
+    e = prob.noise(B, 4, 0).astype(np.float64)
+    eps = 1e-6
+    for b in range(B):
+        J = np.zeros((3, 3))
+        for k in range(3):
+            zp, zm = z[b:b + 1].astype(np.float64).copy(), z[b:b + 1].astype(np.float64).copy()
+            zp[0, k] += eps; zm[0, k] -= eps
+            J[:, k] = (mlp64(p.astype(np.float64), zp) - mlp64(p.astype(np.float64), zm))[0] / (2 * eps)
+        tr = np.trace(J) if not monte_carlo else e[b] @ J @ e[b]
+        assert abs(-out[b, 3] - tr) <= 1e-4 * max(1.0, abs(tr))
+        assert abs(out[b, 4] - np.sum(out[b, :3].astype(np.float64) ** 2)) <= 1e-5 * max(1.0, out[b, 4])
+        assert abs(out[b, 5] - np.linalg.norm(e[b] @ J)) <= 1e-4 * max(1.0, out[b, 5])
+    lam = rng.standard_normal((B, 6)).astype(np.float32)
+    o2, ybar, pbar = prob.vjp(p, y, lam, 4, 0)
+    assert np.array_equal(o2, out) and np.all(ybar[:, 3:] == 0)
+    prob64 = node.FfjordProblem(mlp64, seed=1, monte_carlo=monte_carlo, regularize=True)
+
+    def phi(zz, pp):
+        yy = np.concatenate([zz, np.zeros((B, 3))], 1)
+        o, _ = prob64.f(pp, yy, 4, 0)
+        return float(np.sum(lam.astype(np.float64) * o))
+    h = 1e-5
+    z64, p64 = z.astype(np.float64), p.astype(np.float64)
+    for (b, k) in ((0, 0), (3, 2), (4, 1)):
+        zp, zm = z64.copy(), z64.copy()
+        zp[b, k] += h; zm[b, k] -= h
+        fd = (phi(zp, p64) - phi(zm, p64)) / (2 * h)
+        assert abs(fd - ybar[b, k]) <= 2e-3 * max(1.0, abs(fd)), (fd, ybar[b, k])
+    for i in (0, 7, 20, p.size - 1):
+        pp, pm = p64.copy(), p64.copy()
+        pp[i] += h; pm[i] -= h
+        fd = (phi(z64, pp) - phi(z64, pm)) / (2 * h)
+        assert abs(fd - pbar[i]) <= 2e-3 * max(1.0, abs(fd)), (i, fd, pbar[i])
