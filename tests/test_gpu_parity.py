@@ -678,8 +678,10 @@ def test_ffjord_exact_trace():
 def test_ffjord_regularize(monte_carlo):
     """N4: FFJORD with regularize = true (src/ffjord.jl:131-133,149-153,164-166; test/AdvancedNeuralDE/cnf_tests.jl:34-38):
     the state carries sum(abs2, m(z)) and ||e^T J||_2 integrals.  Forward state, logpx and the gradient of a loss that uses
-    logpx AND both regulariser rows (cotangent on the whole end state) against the oracle; the layer call returns
-    (logpx, lambda_1, lambda_2) with the reference's own slicing and backpropagates through all three."""
+    logpx AND both regulariser rows (cotangent on the whole end state) against the oracle, with one noise draw per solve
+    (noise_per_call = 0: a smooth RHS, so tolerance 1e-6 and exact step counts; with the reference's fresh noise per RHS call
+    the ||e^T J|| row is a random process and the controller takes ~400 noise-limited steps).  Then the layer call with fresh
+    noise: (logpx, lambda_1, lambda_2) sliced as the reference slices them, autograd through all three."""
     import torch
     rng = np.random.default_rng(21)
     D = 3
@@ -687,8 +689,8 @@ def test_ffjord_regularize(monte_carlo):
     p = mlp.init(rng, scale=1.0)
     B = 300
     x = rng.standard_normal((B, D)).astype(np.float32)
-    tol = dict(abstol=1e-6, reltol=1e-6) if not monte_carlo else dict(abstol=1e-3, reltol=1e-3)
-    prob = onode.FfjordProblem(mlp, seed=5, monte_carlo=monte_carlo, regularize=True)
+    tol = dict(abstol=1e-6, reltol=1e-6)
+    prob = onode.FfjordProblem(mlp, seed=5, monte_carlo=monte_carlo, regularize=True, noise_per_call=False)
     fw = onode.forward(prob, p, np.concatenate([x, np.zeros((B, 3), np.float32)], 1), 0.0, 0.5, save_everystep=False,
                        save_start=False, dense=True, **tol)
     g = np.cos(np.arange(B, dtype=np.float32))
@@ -699,37 +701,38 @@ def test_ffjord_regularize(monte_carlo):
     dL[:, D + 1:] = 0
     adj = onode.adjoint(prob, p, fw, (dL + gz)[None], **tol)
     chain = dfx.Chain(dfx.Dense(D, 16, dfx.tanh), dfx.Dense(16, 16, dfx.tanh), dfx.Dense(16, D))
-    ff = dfx.FFJORD(chain, (0.0, 0.5), (D,), dfx.Tsit5(), **tol)
+    ff = dfx.FFJORD(chain, (0.0, 0.5), (D,), dfx.Tsit5(), noise_per_call=0, **tol)
     st = {"regularize": True, "monte_carlo": monte_carlo, "seed": 5, "calls": 0}
     logpx, back = ff.pullback(x, p, st)
     dx, dp = back(g, gz)
     z = np.asarray(ff.last["z"])
     assert z.shape == (B, D + 3)
-    if monte_carlo:
-        check_steps(ff.last["stats"], fw.stats, "regularize forward", False)
-    else:
-        check_steps(ff.last["stats"], fw.stats, "regularize forward", True)
-        assert abs(ff.last["adjoint_stats"].naccept - adj.stats.naccept) <= 1
-    rt = 1e-4 if not monte_carlo else 2e-3                          # (loose tolerance solve: noise amplifies rounding)
-    close(z, fw.us[0], rtol=rt, what="end state")
+    check_steps(ff.last["stats"], fw.stats, "regularize forward", True)
+    # (the backward solve spends most of its ~12 steps ramping up from Hairer's tiny initial dt, where the error estimate
+    # is rounding noise -- DESIGN.md "step-count parity": the count follows the arithmetic's noise floor; gradients below
+    # agree to 1e-6)
+    assert abs(ff.last["adjoint_stats"].naccept - adj.stats.naccept) <= 3
+    close(z, fw.us[0], what="end state")
     assert np.all(z[:, D + 1] > 0) and np.all(z[:, D + 2] > 0)
-    close(np.asarray(logpx).reshape(-1), onode.ffjord_logpx(fw.us[0], D), rtol=rt, what="logpx")
-    close(dx, adj.du0[:, :D], rtol=rt, what="dx")
-    close(dp, adj.dp, rtol=rt, what="dp")
-    # layer protocol + autograd through (logpx, lambda_1, lambda_2)
+    close(np.asarray(logpx).reshape(-1), onode.ffjord_logpx(fw.us[0], D), what="logpx")
+    close(dx, adj.du0[:, :D], what="dx")
+    close(dp, adj.dp, what="dp")
+    # layer protocol with the reference's fresh noise + autograd through (logpx, lambda_1, lambda_2)
+    ff2 = dfx.FFJORD(chain, (0.0, 0.2), (D,), dfx.Tsit5(), abstol=1e-2, reltol=1e-2)
     xt = torch.from_numpy(x).cuda().requires_grad_(True)
     pt = torch.from_numpy(p).cuda().requires_grad_(True)
-    (lp, l1, l2), st2 = ff(xt, pt, st)
+    (lp, l1, l2), st2 = ff2(xt, pt, st)
     assert lp.shape == (1, B) and l1.shape == (1, D + 3) and l2.shape == (1, D + 3) and st2["calls"] == 1
-    zt = ff.last["z"]
+    zt = ff2.last["z"]
     assert torch.equal(l1.detach(), zt[D + 1:D + 2]) and torch.equal(l2.detach(), zt[D + 2:D + 3])
     loss = -(lp.mean()) + 0.5 * l1.sum() + 0.25 * l2.sum()
     loss.backward()
+    _, back2 = ff2.pullback(x, p, st)                              # same seed, same solve
     gz2 = np.zeros((B, D + 3), np.float32)
     gz2[D + 1, :] = 0.5
     gz2[D + 2, :] = 0.25
-    dx2, dp2 = back(np.full(B, -1.0 / B, np.float32), gz2)
+    dx2, dp2 = back2(np.full(B, -1.0 / B, np.float32), gz2)
     close(pt.grad.cpu().numpy(), np.asarray(dp2), rtol=1e-5, what="autograd dp")
     close(xt.grad.cpu().numpy(), np.asarray(dx2), rtol=1e-5, what="autograd dx")
-    smp = ff.backward(64, p, st, rng=np.random.default_rng(0))     # sampling takes the same branch (src/ffjord.jl:194-213)
+    smp = ff2.backward(64, p, st, rng=np.random.default_rng(0))    # sampling takes the same branch (src/ffjord.jl:194-213)
     assert np.asarray(smp).shape == (64, D) and np.isfinite(np.asarray(smp)).all()
