@@ -567,11 +567,17 @@ struct Solver {
   unsigned int tc_g = 0;   // running chunk counter of the tensor-core pipeline (uniform across threads)
   unsigned int tc_wl = 0;  // wgrad layers completed so far (worker side)
   unsigned int tc_wused = 0u, tc_wpar = 0u;   // wgrad operand buffers A0, A1, B0, B1: ever filled / parity of the fill count (bit per buffer)
+#ifdef B200_TC_TRACE
+  unsigned int tr_eval = 0u;
+#define TR_W(on, row, col) { if (on) b200tc::g_tc_trace[0][(row)][(col)] = clock64(); }
+#else
+#define TR_W(on, row, col) {}
+#endif
 #ifdef B200_TC_PROF
   long long pf[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#define PF_T(i, expr) { long long t_ = clock64(); expr; pf[i] += clock64() - t_; }
+#define PF_T(i, ...) { long long t_ = clock64(); __VA_ARGS__; pf[i] += clock64() - t_; }
 #else
-#define PF_T(i, expr) { expr; }
+#define PF_T(i, ...) { __VA_ARGS__; }
 #endif
 
   __device__ Solver(const SolveParams& p, float* s, StepShared& st)

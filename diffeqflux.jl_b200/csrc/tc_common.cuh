@@ -40,6 +40,13 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef B200_TC_TRACE
+// timeline of ONE adjoint stage evaluation of CTA 0 (tools/tc_timeline.py): [0] = worker thread 0, [1] = MMA-issuing thread
+#ifndef B200_TC_TRACE_EVAL
+#define B200_TC_TRACE_EVAL 100
+#endif
+__device__ long long g_tc_trace[2][192][4];
+#endif
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -176,6 +183,28 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+
+// The same MMA issued from a CONVERGED warp: every lane executes the call with warp-uniform operands and one elected
+// lane issues.  With uniform operands ptxas keeps descriptors / addresses in uniform registers; the single-lane form
+// above makes it wrap every UTCHMMA in an elect + 7 x R2UR.BROADCAST + vote loop (~80-160 cycles of issue per MMA).
+__device__ __forceinline__ void mma_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// value of lane 0, known to ptxas as warp-uniform
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 
 // ---- register reallocation between warpgroups (setmaxnreg; executed by every warp of a 4-warp group) -----------
 template <uint32_t R>
