@@ -549,6 +549,8 @@ struct StepShared {
   TcOp ops[TC_MAX_OPS];
   TcLoad loads[TC_MAX_LOADS];
   float bias_acc[4][TC_MAX_BIAS];        // per TMEM quadrant partial column sums of the cotangents
+  alignas(16) float tc_bias[TC_MAX_BIAS]; // the layers' biases back to back (layer l at sum_{i<l} dims[i+1]): read once per chunk by
+                                         // every worker, on the MMA's critical path (a global load there is an L2 round trip)
 };
 
 template <int FL>
@@ -1602,21 +1604,29 @@ struct Solver {
   // slices of MU_CB CTAs at a time staged in the (idle) operand buffers by cp.async.bulk -- the copy engine
   // keeps ~170 KB in flight per SM where register-held loads reach ~30 GB/s per SM.  Thread t gets elements
   // slo + t + k*NTHREADS.  Sums over CTAs run in fp64 in CTA order (deterministic).
-  static constexpr int MU_SUB = 1024, MU_CB = 3;
+  static constexpr int MU_SUB = 1024;
+  static constexpr int MU_STAGE_BYTES = 2 * TC_A_SLOT + TC_NB * TC_B_SLOT;      // the operand buffers, idle in the mu phase
   unsigned int mu_use[2] = {0u, 0u};
   __device__ void step_staged(int slo, int n, int g1, int g7, double (&T0)[MU_SUB / NTHREADS], double (&T1)[MU_SUB / NTHREADS]) {
     using namespace b200tc;
     const int pp = P.mlp.ppad;
     float* stage = reinterpret_cast<float*>(tc_base());
-    constexpr int BUF = MU_CB * NSTEP_SLAB * MU_SUB;  // floats per staging buffer
-    const int nb = (P.nctas + MU_CB - 1) / MU_CB;
+    // two staging buffers; each holds the 7 slab slices (n floats, row pitch nst) of `cb` CTAs
+#ifdef B200_MU_ADAPTIVE     // (measured slower: 31.0 vs 30.65 ms -- the 3088-byte row pitch costs more than the 25 % fewer batches save)
+    const int nst = (n + 3) & ~3;
+    const int cb = max(1, min(NTHREADS / NSTEP_SLAB, (MU_STAGE_BYTES / 2) / (NSTEP_SLAB * nst * 4)));
+#else
+    const int nst = MU_SUB, cb = 3;
+#endif
+    const int BUF = cb * NSTEP_SLAB * nst;            // floats per staging buffer
+    const int nb = (P.nctas + cb - 1) / cb;
     auto issue = [&](int b) {                         // all threads: one copy each (a single issuing thread spent
-      const int buf = b & 1, c0 = b * MU_CB, cn = min(MU_CB, P.nctas - c0);   // ~1/3 of the phase issuing 21 copies per batch)
+      const int buf = b & 1, c0 = b * cb, cn = min(cb, P.nctas - c0);   // ~1/3 of the phase issuing the copies of a batch)
       uint64_t* bar = reinterpret_cast<uint64_t*>(&ss.mu_full[buf]);
       if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(cn * NSTEP_SLAB * n * 4));
       if (tid < cn * NSTEP_SLAB) {
         const int c = tid / NSTEP_SLAB, sl = tid - c * NSTEP_SLAB;
-        bulk_g2s(stage + buf * BUF + (c * NSTEP_SLAB + sl) * MU_SUB, P.slabs + ((long long)(c0 + c) * NSLAB + sl) * pp + slo,
+        bulk_g2s(stage + buf * BUF + (c * NSTEP_SLAB + sl) * nst, P.slabs + ((long long)(c0 + c) * NSLAB + sl) * pp + slo,
                  (uint32_t)(n * 4), bar);
       }
     };
@@ -1625,7 +1635,7 @@ struct Solver {
 #pragma unroll
     for (int k = 0; k < MU_SUB / NTHREADS; ++k) T0[k] = T1[k] = 0.0;
     for (int b = 0; b < nb; ++b) {
-      const int buf = b & 1, cn = min(MU_CB, P.nctas - b * MU_CB);
+      const int buf = b & 1, cn = min(cb, P.nctas - b * cb);
       tc_wait_bar(&ss.mu_full[buf], mu_use[buf] & 1u);
       mu_use[buf] += 1u;
       const float* sb = stage + buf * BUF;
@@ -1634,12 +1644,12 @@ struct Solver {
         for (int k = 0; k < MU_SUB / NTHREADS; ++k) {
           const int jj = tid + k * NTHREADS;
           if (jj < n) {
-            const float* q = sb + c * NSTEP_SLAB * MU_SUB + jj;
-            const float k1 = q[g1 * MU_SUB], k7 = q[g7 * MU_SUB];
+            const float* q = sb + c * NSTEP_SLAB * nst + jj;
+            const float k1 = q[g1 * nst], k7 = q[g7 * nst];
             float a = c_tab.a[6][0] * k1, e = c_tab.bt[0] * k1;
 #pragma unroll
             for (int s5 = 0; s5 < 5; ++s5) {
-              const float ks = q[s5 * MU_SUB];
+              const float ks = q[s5 * nst];
               a = fmaf(c_tab.a[6][1 + s5], ks, a);
               e = fmaf(c_tab.bt[1 + s5], ks, e);
             }
