@@ -83,7 +83,7 @@ def tf32_peak():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE adjoint solve-kernel launch at this workload (ncu --set full capture of
 # this round's build, profiles/solve_kernels_r2_tc_raw.csv, second row); algorithmic bytes are ~0 (the path is tensor bound)
-ADJ_DRAM_BYTES_PER_LAUNCH = 29.438428e9 + 28.156291e9
+ADJ_DRAM_BYTES_PER_LAUNCH = 29.147705e9 + 28.179562e9
 
 
 def golden_steps():

@@ -1,10 +1,11 @@
 #!/bin/bash
 # ncu --set full captures of every persistent-kernel flavour (tools/profile_kernels.py), exported as raw-page CSV under
-# gpurun_out/ (the .ncu-rep files are deleted: gpurun copies back at most 64 MiB).  usage: tools/ncu_capture.sh [tag]
+# gpurun_out/ (the .ncu-rep files are deleted: gpurun copies back at most 64 MiB).  usage: tools/ncu_capture.sh [tag] [parts, default "tc ffma ffjord"]
 tag=${1:-r2}
 out=gpurun_out
 mkdir -p $out
-for part in tc ffma ffjord; do
+parts=${2:-"tc ffma ffjord"}
+for part in $parts; do
   n=4; [ $part = ffjord ] && n=2
   src=""; [ $part = tc ] && src="--import-source on"
   timeout 600 ncu --set full --clock-control none $src -k regex:solve_kernel -c $n -o $out/ncu_${part}_$tag -f python tools/profile_kernels.py $part > $out/ncu_${part}_$tag.log 2>&1
