@@ -480,7 +480,7 @@ __global__ void strided_copy_kernel(PermDesc d, const float* __restrict__ in, fl
 }
 
 // ------------------------------------------------------------------------------------------------ planning
-static int plan_smem(const MlpDesc& m, int flavor, int TB, SmemPlan& sp) {
+static int plan_smem(const MlpDesc& m, int flavor, int TB, SmemPlan& sp, bool rowthread = false) {
   memset(&sp, 0, sizeof sp);
   int off = 0;
   auto take = [&](int floats_per_row) {
@@ -496,6 +496,13 @@ static int plan_smem(const MlpDesc& m, int flavor, int TB, SmemPlan& sp) {
     for (int l = 0; l < m.nl; ++l) sp.hd_off[l] = take(m.dpad[l]);
     for (int l = 1; l < m.nl; ++l) sp.q_off[l] = take(m.dpad[l]);
     sp.ll_off = take(4);
+  }
+  if (rowthread) {                       // row-per-thread FFJORD forward: weights + biases and the transposed weights
+    sp.roww_off = off;
+    off += m.ppad;
+    sp.rowwt_off = off;
+    off += m.wt_off[m.nl - 1] + m.dpad[m.nl] * m.dpad[m.nl - 1];
+    off = (off + 3) & ~3;
   }
   sp.total = off;
   return off * (int)sizeof(float);
@@ -580,7 +587,7 @@ static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int ti
   } else if (rowthread_eligible(m, flavor)) {
     // one thread per trajectory: a tile is as many rows as the CTA has threads (fewer for small batches)
     for (int TB = NTHREADS; TB >= 32; TB >>= 1) {
-      if (plan_smem(m, flavor, TB, sp) > budget) continue;
+      if (plan_smem(m, flavor, TB, sp, true) > budget) continue;
       best = TB;
       if ((B + TB - 1) / TB >= ctx->num_sms || TB == 32) break;     // keep every SM busy before growing the tile
     }
@@ -598,8 +605,8 @@ static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int ti
                      "model too wide for the shared-memory resident path (8 rows need %d B > %d B)",
                      plan_smem(m, flavor, 8, sp), budget);
   }
-  *smem_bytes = plan_smem(m, flavor, best, P.sp);
   P.rowthread = (tile_opt <= 0 && rowthread_eligible(m, flavor)) ? 1 : 0;
+  *smem_bytes = plan_smem(m, flavor, best, P.sp, P.rowthread != 0);
   P.TB = best;
   P.ntiles = (B + best - 1) / best;
   int per_sm = 0;

@@ -57,6 +57,7 @@ struct SmemPlan {
   int dl2_off;            // second seed (hdbar_L, FFJORD adjoint) or m(z) (FFJORD forward)
   int x_off;              // raw input when a cube pre-layer is present
   int ll_off;             // lambda_logp per row (FFJORD adjoint)
+  int roww_off, rowwt_off;// row-per-thread FFJORD forward: the packed parameters / transposed weights staged once per solve
   int total;              // floats
 };
 
@@ -1096,11 +1097,19 @@ struct Solver {
   // trajectory t of the tile: its 64 accumulators live in registers, the weight rows are warp-uniform (broadcast)
   // 16-byte loads through L1, hidden activations go through shared memory column-major ([feature][row]: conflict free),
   // and no barrier separates the layers.  acc[n] (+)= x * W[n .. ] for NQ quads of outputs.
+  // (the weights are in shared memory: stage_row_weights; a warp-uniform 16-byte LDS per four FMAs)
+  __device__ void stage_row_weights() {
+    const MlpDesc& M = P.mlp;
+    const int L = M.nl, nwt = M.wt_off[L - 1] + M.dpad[L] * M.dpad[L - 1];
+    for (int i = tid; i < M.ppad; i += NTHREADS) sm[P.sp.roww_off + i] = P.wp[i];
+    for (int i = tid; i < nwt; i += NTHREADS) sm[P.sp.rowwt_off + i] = P.wtp[i];
+    sync();
+  }
   template <int NQ>
   __device__ __forceinline__ void row_axpy(float (&acc)[64], float x, const float* __restrict__ wrow) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(wrow) + q);
+      const float4 w = *(reinterpret_cast<const float4*>(wrow) + q);
       acc[4 * q + 0] = fmaf(x, w.x, acc[4 * q + 0]);
       acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
       acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]);
@@ -1144,15 +1153,15 @@ struct Solver {
       // ---- forward: h_{l+1} = act(h_l W_l + b_l); hidden h_l kept column-major in the act_off[l] buffer
       for (int l = 0; l < L; ++l) {
         const int K = M.dims[l], Np = M.dpad[l + 1], N = M.dims[l + 1], nq = Np >> 2;
-        const float* bias = P.wp + M.b_off[l];
+        const float* bias = sm + P.sp.roww_off + M.b_off[l];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < nq) b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+          if (q < nq) b = *(reinterpret_cast<const float4*>(bias) + q);
           acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w;
         }
-        if (l == 0) row_matvec(acc, sm + P.sp.act_off[0] + t * M.dpad[0], 1, K, P.wp + M.w_off[0], Np, nq);
-        else row_matvec(acc, sm + P.sp.act_off[l] + t, TB, K, P.wp + M.w_off[l], Np, nq);
+        if (l == 0) row_matvec(acc, sm + P.sp.act_off[0] + t * M.dpad[0], 1, K, sm + P.sp.roww_off + M.w_off[0], Np, nq);
+        else row_matvec(acc, sm + P.sp.act_off[l] + t, TB, K, sm + P.sp.roww_off + M.w_off[l], Np, nq);
         const int a = M.act[l];
         if (l < L - 1) {
           float* H = sm + P.sp.act_off[l + 1] + t;
@@ -1178,8 +1187,8 @@ struct Solver {
         const int N = M.dims[l + 1], Kp = M.dpad[l], K = M.dims[l], kq = Kp >> 2;
 #pragma unroll
         for (int n = 0; n < 64; ++n) acc[n] = 0.f;
-        if (l == L - 1) row_matvec(acc, e + t * Lp, 1, N, P.wtp + M.wt_off[l], Kp, kq);
-        else row_matvec(acc, sm + P.sp.act_off[l + 1] + t, TB, N, P.wtp + M.wt_off[l], Kp, kq);
+        if (l == L - 1) row_matvec(acc, e + t * Lp, 1, N, sm + P.sp.rowwt_off + M.wt_off[l], Kp, kq);
+        else row_matvec(acc, sm + P.sp.act_off[l + 1] + t, TB, N, sm + P.sp.rowwt_off + M.wt_off[l], Kp, kq);
         if (l > 0) {
           const int a = M.act[l - 1];
           float* H = sm + P.sp.act_off[l] + t;

@@ -63,6 +63,9 @@ __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParam
   long long qf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long qf_start = clock64();
 #endif
+  if constexpr (FL == FL_FWD_FFJORD) {
+    if (P.rowthread) S.stage_row_weights();
+  }
   // ------------------------------------------------------------------ initial state (slot 0)
   float* U0 = S.slotv(0, 0);
   S.for_my_tiles([&](int tile) {
