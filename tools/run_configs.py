@@ -104,6 +104,8 @@ def main():
     out.append({"config": "cfg4 multiple_shoot 32->128->128->32, 16 groups x 4096, group_size 5 (groups run concurrently, 4 at a time)", "B": B * len(run.stats), "groups": len(run.stats),
                 "evals_per_s": B * nf / wall, "wall_ms": wall * 1e3, "kernel_ms": kms, "loss": float(loss), "retcode": int(run.retcode)})
     for o in out:
+        if o.get("fwd") and o.get("adj"):       # rate over the kernels' own time (wall clock of one pass includes host set-up)
+            o["evals_per_s_kernel_time"] = o["B"] * (o["fwd"][2] + o["adj"][2]) / (o["kernel_ms"] * 1e-3)
         print(json.dumps(o))
 
 
