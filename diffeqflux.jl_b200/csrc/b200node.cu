@@ -568,15 +568,26 @@ static bool rowthread_eligible(const MlpDesc& m, int flavor) {
     if (m.dpad[l] > 64) return false;
   return true;
 }
+static int max_width(const MlpDesc& m) {
+  int w = 0;
+  for (int l = 0; l <= m.nl; ++l) w = std::max(w, m.dpad[l]);
+  return w;
+}
+// every width <= 64 and enough trajectories to give each SM a 128-row tile: the tile engine at TB = 128 beats both its
+// own smaller tiles and the row-per-thread RHS (218 vs 249 ms on the cfg 3 forward)
+static bool narrow_full_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B) {
+  return (flavor == FL_FWD_FFJORD || flavor == FL_ADJ_FFJORD) && max_width(m) <= 64 && B >= 128 * ctx->num_sms;
+}
 // choose the tile (trajectories per CTA pass) and the grid
 static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int tile_opt, SolveParams& P,
-                      int* smem_bytes) {
+                      int* smem_bytes, bool exact_trace = false) {
   int static_bytes = 0;                        // static __shared__ StepShared lives beside the dynamic part
   if (cudaFuncAttributes_ok(static_smem_any(flavor, &static_bytes)) != 0)
     return set_err(ctx, B200_ERR_CUDA, "cudaFuncGetAttributes failed");
   const int budget = ctx->smem_optin - static_bytes;
   int best = 0;
   double best_cost = 1e300;
+  bool rows = false;
   SmemPlan sp;
   if (tile_opt > 0) {
     if (tile_opt % 8) return set_err(ctx, B200_ERR_ARG, "opts.tile must be a multiple of 8");
@@ -584,7 +595,8 @@ static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int ti
       return set_err(ctx, B200_ERR_UNSUPPORTED, "opts.tile=%d needs %d B of shared memory (> %d)", tile_opt,
                      plan_smem(m, flavor, tile_opt, sp), budget);
     best = tile_opt;
-  } else if (rowthread_eligible(m, flavor)) {
+  } else if (rowthread_eligible(m, flavor) && (exact_trace || !narrow_full_tiles(ctx, m, flavor, B))) {
+    rows = true;
     // one thread per trajectory: a tile is as many rows as the CTA has threads (fewer for small batches)
     for (int TB = NTHREADS; TB >= 32; TB >>= 1) {
       if (plan_smem(m, flavor, TB, sp, true) > budget) continue;
@@ -597,7 +609,11 @@ static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int ti
       if (plan_smem(m, flavor, TB, sp) > budget) continue;
       const int ntiles = (B + TB - 1) / TB;
       const int waves = (ntiles + ctx->num_sms - 1) / ctx->num_sms;
-      const double cost = (double)waves * std::max(TB, 32);
+      double cost = (double)waves * std::max(TB, 32);
+      // narrow networks with plenty of rows: a tile's GEMM is (TB/8) x (width/4) register tiles over NTHREADS threads -- below
+      // one per thread the idle threads are paid for (measured, cfg 3 FFJORD 2->64->64->2 at B = 65536: TB = 64 forward
+      // 323 ms / adjoint 43.1 ms, TB = 128 218 ms / 33.7 ms)
+      if (narrow_full_tiles(ctx, m, flavor, B)) cost /= std::min(1.0, (TB / 8) * (max_width(m) / 4) / (double)NTHREADS);
       if (cost < best_cost) { best_cost = cost; best = TB; }
     }
     if (!best)
@@ -605,7 +621,7 @@ static int plan_tiles(b200_ctx* ctx, const MlpDesc& m, int flavor, int B, int ti
                      "model too wide for the shared-memory resident path (8 rows need %d B > %d B)",
                      plan_smem(m, flavor, 8, sp), budget);
   }
-  P.rowthread = (tile_opt <= 0 && rowthread_eligible(m, flavor)) ? 1 : 0;
+  P.rowthread = rows ? 1 : 0;
   *smem_bytes = plan_smem(m, flavor, best, P.sp, P.rowthread != 0);
   P.TB = best;
   P.ntiles = (B + best - 1) / best;
@@ -771,7 +787,7 @@ static int forward_core(b200_ctx* ctx, const b200_model* model, int flavor, cons
     t->tc.wimg_t = want_t ? t->wimg + fwd_bytes : nullptr;
     pack_tc_kernel<<<dim3(64, m.nl), 256, 0, ctx->stream>>>(m, t->tc, p_dev, t->wimg);
     if (want_t) pack_tc_t_kernel<<<dim3(64, m.nl), 256, 0, ctx->stream>>>(m, t->tc, p_dev, t->wimg + fwd_bytes);
-  } else if ((rc = plan_tiles(ctx, m, flavor, B, o->tile, P, &smem_bytes)) != 0) return fail(rc);
+  } else if ((rc = plan_tiles(ctx, m, flavor, B, o->tile, P, &smem_bytes, flavor == FL_FWD_FFJORD && o->ffjord_exact_trace)) != 0) return fail(rc);
   P.tc = t->tc;
 
   // dense tape capacity
