@@ -10,7 +10,7 @@ p, rng = mlp_params(dims, 3, 0.5)
 B = 65536
 x = rng.standard_normal((B, 2)).astype(np.float32)
 st = {"regularize": False, "monte_carlo": True, "seed": 3, "calls": 0}
-for tile in (0, 32, 64, 128):
+for tile in (0, 128, 256):
     kw = dict(tile=tile) if tile else {}
     ff = dfx.FFJORD(chain_of(dims), (0.0, 1.0), (2,), dfx.Tsit5(), abstol=1e-3, reltol=1e-3, maxiters=200000, **kw)
     for r in range(2):
