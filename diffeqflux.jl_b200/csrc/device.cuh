@@ -273,6 +273,27 @@ __device__ __forceinline__ float tanh_fast(float x) {
   const float b = copysignf(fmaf(-2.f, r, 1.f), x);
   return t < 0.35f ? p : b;
 }
+// Same function with ONE MUFU op per value: the reciprocal of e + 1 (>= 2) by three Newton steps from a bit-trick seed
+// (12 % -> 1.4e-2 -> 2e-4 -> 4e-8 relative) instead of MUFU.RCP.  For the tensor-core engine's epilogues, where the two
+// worker warps of a scheduler hit the 4-lane MUFU unit at the same moment (-DB200_TC_TANH_NR).
+__device__ __forceinline__ float tanh_fast_nr(float x) {
+  const float t = fminf(fabsf(x), 10.f);          // tanh(10) rounds to 1; keeps e + 1 finite
+  const float x2 = x * x;
+  float p = fmaf(x2, -8.8632355e-3f, 2.1869488e-2f);
+  p = fmaf(x2, p, -5.3968254e-2f);
+  p = fmaf(x2, p, 1.3333334e-1f);
+  p = fmaf(x2, p, -3.3333334e-1f);
+  p = fmaf(x * x2, p, x);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * 2.8853900817779268f));
+  const float d = e + 1.f;
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  const float b = copysignf(fmaf(-2.f, r, 1.f), x);
+  return t < 0.35f ? p : b;
+}
 __device__ __forceinline__ float act_apply_fast(int a, float x) { return a == ACT_TANH ? tanh_fast(x) : act_apply(a, x); }
 // act'(pre) written in terms of h = act(pre)
 __device__ __forceinline__ float act_d1(int a, float h) {
