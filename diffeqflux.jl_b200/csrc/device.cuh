@@ -555,6 +555,10 @@ struct StepShared {
   // tensor-core engine: mbarriers
   unsigned long long a_full[2];          // (TC_WORKERS arrivals) the workers filled A slot s
   unsigned long long mma_done[2];        // MMAs that read A slot s have completed
+  // -DB200_TC_HALF_BARRIERS: the same pair per 16-column half of a slot (half h is filled by worker warpgroup h and read by
+  // the K16 group hh = h of the chunk's MMAs): the two warpgroups stop waiting for each other and run half a chunk apart
+  unsigned long long a_fullh[2][2];
+  unsigned long long mma_doneh[2][2];
   unsigned long long unit_done[TC_NB];   // MMAs that read weight slot s have completed
   unsigned long long b_full[TC_NB];      // weight unit landed in slot s
   unsigned long long w_full[4];          // (TC_WORKERS arrivals) wgrad operand buffer filled by the workers (A0, A1, B0, B1)
