@@ -736,3 +736,33 @@ def test_ffjord_regularize(monte_carlo):
     close(xt.grad.cpu().numpy(), np.asarray(dx2), rtol=1e-5, what="autograd dx")
     smp = ff2.backward(64, p, st, rng=np.random.default_rng(0))    # sampling takes the same branch (src/ffjord.jl:194-213)
     assert np.asarray(smp).shape == (64, D) and np.isfinite(np.asarray(smp)).all()
+
+
+def test_ffjord_many_rows_uses_full_tiles():
+    """FFJORD with a narrow network and >= 128 trajectories per SM: the planner gives forward and adjoint 128-row tiles (a
+    tile's GEMM is (TB/8) x (width/4) register tiles over 256 threads: smaller tiles leave threads idle) instead of the
+    row-per-thread RHS / 64-row tiles.  Same noise stream (it is indexed by the global trajectory), so the oracle
+    comparison of test_ffjord_gradients_large_batch carries over: exact step counts, logpx / dx / dp within 1e-4."""
+    import torch
+    nsm = torch.cuda.get_device_properties(0).multi_processor_count
+    rng = np.random.default_rng(16)
+    mlp = MLP([2, 16, 16, 2], [ACT_TANH, ACT_TANH, ACT_ID])
+    p = mlp.init(rng, scale=0.5)
+    B = 128 * nsm + 37
+    x = rng.standard_normal((B, 2)).astype(np.float32)
+    tol = dict(abstol=1e-3, reltol=1e-3)
+    prob = onode.FfjordProblem(mlp, seed=9)
+    fw = onode.forward(prob, p, np.concatenate([x, np.zeros((B, 1), np.float32)], 1), 0.0, 0.5, save_everystep=False,
+                       save_start=False, dense=True, **tol)
+    g = np.full(B, -1.0 / B, np.float32)
+    adj = onode.adjoint(prob, p, fw, onode.ffjord_logpx_grad(fw.us[0], 2, g)[None], **tol)
+    chain = dfx.Chain(dfx.Dense(2, 16, dfx.tanh), dfx.Dense(16, 16, dfx.tanh), dfx.Dense(16, 2))
+    ff = dfx.FFJORD(chain, (0.0, 0.5), (2,), dfx.Tsit5(), **tol)
+    logpx, back = ff.pullback(x, p, {"regularize": False, "monte_carlo": True, "seed": 9, "calls": 0})
+    dx, dp = back(g)
+    assert ff.last["stats"].tile == 128 and ff.last["adjoint_stats"].tile == 128
+    check_steps(ff.last["stats"], fw.stats, "ffjord forward", True)
+    check_steps(ff.last["adjoint_stats"], adj.stats, "ffjord adjoint", True)
+    close(np.asarray(logpx).reshape(-1), onode.ffjord_logpx(fw.us[0], 2), what="logpx")
+    close(dx, adj.du0[:, :2], what="dx")
+    close(dp, adj.dp, what="dp")
