@@ -13,7 +13,11 @@ namespace b200 {
 // The FFJORD forward is compiled for two CTAs per SM (128 registers, ~0.5 KB of spills): its tile engine stalls 31 % of
 // the time at the per-layer CTA barriers, which a second resident CTA hides (cfg 3 forward 219 -> 147 ms); its shared-
 // memory plan (72 KB at 128-row tiles of 64-wide networks) leaves room for two.  Every other flavour needs the registers.
+#ifdef B200_FFMA_OCC2            // experiment: every FP32-FFMA flavour at 128 registers
+#define B200_KERNEL_ATTR __launch_bounds__(NTHREADS, 2)
+#else
 #define B200_KERNEL_ATTR __launch_bounds__(NTHREADS, (FL == FL_FWD_FFJORD ? 2 : 1))
+#endif
 #endif
 template <int FL, bool TC = false>
 __global__ void B200_KERNEL_ATTR solve_kernel(const __grid_constant__ SolveParams P) {
