@@ -29,3 +29,19 @@ node = dfx.NeuralODE(chain([2, 16, 2]), (0.0, 0.5), dfx.Tsit5(), saveat=np.linsp
 pp = params([2, 16, 2]); opt = dfx.AdamState()
 print("train", dfx.train_step(node, np.ones((3, 2), np.float32), pp, np.zeros((4, 3, 2), np.float32), opt))
 print("dimmover", dfx.DimMover()(rng.standard_normal((4, 3, 2)).astype(np.float32))[0].shape)
+
+# FFJORD regularize (both trace modes) and the many-rows tile path (two CTAs per SM)
+dims = [3, 16, 16, 3]
+p = params(dims, 1.0)
+for mc in (True, False):
+    x = rng.standard_normal((77, 3)).astype(np.float32)
+    ff = dfx.FFJORD(chain(dims), (0.0, 0.3), (3,), dfx.Tsit5(), abstol=1e-3, reltol=1e-3, noise_per_call=0)
+    lp, back = ff.pullback(x, p, {"regularize": True, "monte_carlo": mc, "seed": 1, "calls": 0})
+    gz = np.zeros((77, 6), np.float32); gz[:, 4] = 0.5; gz[:, 5] = 0.25
+    dx, dp = back(np.ones(77, np.float32), gz)
+    print("ffjord regularize", mc, float(np.abs(dp).sum()), flush=True)
+x = rng.standard_normal((128 * 148 + 5, 3)).astype(np.float32)
+ff = dfx.FFJORD(chain(dims), (0.0, 0.2), (3,), dfx.Tsit5(), abstol=1e-2, reltol=1e-2)
+lp, back = ff.pullback(x, p, {"regularize": False, "monte_carlo": True, "seed": 1, "calls": 0})
+dx, dp = back(np.ones(x.shape[0], np.float32))
+print("ffjord many rows", ff.last["stats"].tile, ff.last["stats"].grid, ff.last["adjoint_stats"].tile, float(np.abs(dp).sum()), flush=True)
